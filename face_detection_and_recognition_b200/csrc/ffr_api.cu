@@ -1,0 +1,492 @@
+// C-ABI entry points of libffr_b200.so (declared in include/ffr.h): argument checking, dispatch between
+// the exact fp32 CUDA-core kernel and the tcgen05 kernel, workspace carving, the host-buffer pipeline
+// (ffr_ctx_*) and the NCCL gather (ffr_comm_*, NCCL dlopen'ed so the library loads without it).
+#include <dlfcn.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "ffr_common.cuh"
+
+#define FFR_STR2(x) #x
+#define FFR_STR(x) FFR_STR2(x)
+
+namespace ffr {
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+float g_delta = 4e-4f;       // recheck window in cosine units, see DESIGN.md §4 (fp16 operand rounding)
+struct LastCall { const void* ws; int path; int launches; };
+thread_local LastCall g_last = {nullptr, 0, 0};
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return FFR_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t hdr, ref16, cand16, recs, total;
+    bool mma;
+};
+
+bool mma_eligible(int64_t n_ref, int32_t dim, int metric, int flags) {
+    if (metric != FFR_METRIC_COSINE) return false;
+    if (flags & FFR_FLAG_FORCE_FP32) return false;
+    if (dim > 512) return false;
+    if (flags & FFR_FLAG_FORCE_MMA) return true;
+    return n_ref > 8;          // <= 8 references: the streaming fp32 kernel is already HBM-bound and exact
+}
+
+WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool mma) {
+    WsLayout L{};
+    L.mma = mma;
+    size_t off = 0;
+    L.hdr = off; off += align_up(sizeof(WsHeader), 256);
+    if (mma) {
+        const size_t ld = static_cast<size_t>(ffr_padded_dim(dim));
+        L.ref16 = off;  if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_ref) * ld * 2, 256);
+        L.cand16 = off; if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_cand) * ld * 2, 256);
+        L.recs = off;   off += align_up(static_cast<size_t>(n_cand) * sizeof(RecheckRec), 256);
+    }
+    L.total = off;
+    return L;
+}
+
+int check_common(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype, int metric,
+                 const uint8_t* keep, const int32_t* idx) {
+    if (n_ref <= 0) { set_error("n_ref must be > 0 (got %lld)", (long long)n_ref); return FFR_ERR_INVALID; }
+    if (n_cand < 0) { set_error("n_cand must be >= 0 (got %lld)", (long long)n_cand); return FFR_ERR_INVALID; }
+    if (dim <= 0) { set_error("dim must be > 0 (got %d)", dim); return FFR_ERR_INVALID; }
+    if (ref == nullptr || (n_cand > 0 && (cand == nullptr || keep == nullptr || idx == nullptr))) {
+        set_error("null pointer argument");
+        return FFR_ERR_INVALID;
+    }
+    if (dtype != FFR_DTYPE_F32 && dtype != FFR_DTYPE_F16) { set_error("unknown dtype %d", dtype); return FFR_ERR_INVALID; }
+    if (metric != FFR_METRIC_COSINE && metric != FFR_METRIC_EUCLID) { set_error("unknown metric %d", metric); return FFR_ERR_INVALID; }
+    return FFR_OK;
+}
+
+// core: ref16_pre != nullptr -> references already normalised/converted (ctx pipeline caches them)
+int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim,
+                int dtype, int metric, float thr, int64_t ref_index_base, uint8_t* keep, int32_t* best_idx,
+                float* best_val, float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, int flags,
+                void* workspace, size_t ws_bytes, cudaStream_t s) {
+    const bool mma = mma_eligible(n_ref, dim, metric, flags);
+    if ((flags & FFR_FLAG_FORCE_MMA) && !mma) {
+        set_error("FFR_FLAG_FORCE_MMA: tcgen05 path needs metric cosine and dim <= 512 (dim=%d metric=%d)", dim, metric);
+        return FFR_ERR_UNSUPPORTED;
+    }
+    const WsLayout L = ws_layout(ref16_pre ? 0 : n_ref, n_cand, dim, dtype, mma);
+    if (workspace == nullptr || ws_bytes < L.total) {
+        set_error("workspace too small: need %zu bytes, got %zu", L.total, workspace ? ws_bytes : (size_t)0);
+        return FFR_ERR_WORKSPACE;
+    }
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("workspace must be 256-byte aligned"); return FFR_ERR_INVALID; }
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(ws + L.hdr);
+    g_last = {workspace, mma ? 1 : 0, 0};
+    if (band_count != nullptr) FFR_CUDA_TRY(cudaMemsetAsync(band_count, 0, sizeof(int32_t), s));
+    FFR_CUDA_TRY(cudaMemsetAsync(hdr, 0, sizeof(WsHeader), s));
+    if (n_cand == 0) return FFR_OK;
+
+    if (!mma) {
+        if (dtype != FFR_DTYPE_F32) {
+            set_error("fp16 inputs are only accepted by the tcgen05 cosine path (n_ref > 8, dim <= 512)");
+            return FFR_ERR_UNSUPPORTED;
+        }
+        g_last.launches = 1;
+        return launch_filter_fp32(static_cast<const float*>(ref), n_ref, static_cast<const float*>(cand), n_cand, dim,
+                                  metric, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
+                                  band_rows, band_cap, s);
+    }
+
+    const int32_t ld = ffr_padded_dim(dim);
+    const __half* ref16 = ref16_pre;
+    const __half* cand16 = nullptr;
+    int launches = 0;
+    int rc;
+    if (dtype == FFR_DTYPE_F32) {
+        if (ref16 == nullptr) {
+            __half* r16 = reinterpret_cast<__half*>(ws + L.ref16);
+            rc = launch_l2norm(static_cast<const float*>(ref), n_ref, dim, r16, ld, nullptr, nullptr, s);
+            if (rc != FFR_OK) return rc;
+            ref16 = r16;
+            ++launches;
+        }
+        __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
+        rc = launch_l2norm(static_cast<const float*>(cand), n_cand, dim, c16, ld, nullptr, nullptr, s);
+        if (rc != FFR_OK) return rc;
+        cand16 = c16;
+        ++launches;
+    } else {
+        if (ref16 == nullptr) ref16 = static_cast<const __half*>(ref);
+        cand16 = static_cast<const __half*>(cand);
+    }
+    const bool recheck = (dtype == FFR_DTYPE_F32) && !(flags & FFR_FLAG_NO_RECHECK);
+    g_last.launches = launches + 1 + (recheck ? 1 : 0);
+    RecheckRec* recs = reinterpret_cast<RecheckRec*>(ws + L.recs);
+    const float delta = g_delta;
+    float thr_band = delta;
+    if (band_count != nullptr && band_tol + delta > thr_band) thr_band = band_tol + delta;
+    rc = launch_filter_mma(ref16, n_ref, cand16, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
+                           best_val, hdr, recs, n_cand, recheck ? 0 : 1, s);
+    if (rc != FFR_OK) return rc;
+    if (recheck) {
+        rc = launch_recheck(static_cast<const float*>(ref), n_ref, static_cast<const float*>(cand), n_cand, dim, nullptr,
+                            nullptr, thr, ref_index_base, keep, best_idx, best_val, hdr, recs, n_cand, band_tol,
+                            band_count, band_rows, band_cap, s);
+        if (rc != FFR_OK) return rc;
+    }
+    return FFR_OK;
+}
+
+}  // namespace
+}  // namespace ffr
+
+using namespace ffr;
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ffr_abi_version(void) { return FFR_ABI_VERSION; }
+const char* ffr_last_error(void) { return g_err; }
+const char* ffr_build_info(void) {
+    return "libffr_b200: sm_100a (tcgen05/TMEM/TMA), CUDA " FFR_STR(CUDART_VERSION) ", built " __DATE__;
+}
+int ffr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int32_t ffr_padded_dim(int32_t dim) { return (dim + 63) / 64 * 64; }
+int64_t ffr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// not in the public header: tuning / test hooks
+void ffr_set_recheck_delta(float d) { g_delta = d; }
+float ffr_get_recheck_delta(void) { return g_delta; }
+
+int ffr_l2norm_rows_f32(const float* x, int64_t rows, int32_t dim, void* y_f16, int32_t y_f16_ld, float* y_f32,
+                        float* norms, ffr_stream_t stream) {
+    if (rows < 0 || dim <= 0) { set_error("l2norm: rows >= 0 and dim > 0 required"); return FFR_ERR_INVALID; }
+    if (rows == 0) return FFR_OK;
+    if (x == nullptr) { set_error("l2norm: x is null"); return FFR_ERR_INVALID; }
+    if (y_f16 != nullptr && y_f16_ld < dim) { set_error("l2norm: y_f16_ld %d < dim %d", y_f16_ld, dim); return FFR_ERR_INVALID; }
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    return launch_l2norm(x, rows, dim, static_cast<__half*>(y_f16), y_f16_ld, y_f32, norms, static_cast<cudaStream_t>(stream));
+}
+
+size_t ffr_filter_workspace_bytes(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, int metric) {
+    if (n_ref <= 0 || n_cand < 0 || dim <= 0) return 0;
+    // sized for the tcgen05 path whenever it could be chosen (including FFR_FLAG_FORCE_MMA)
+    const bool mma = metric == FFR_METRIC_COSINE && dim <= 512;
+    return ws_layout(n_ref, n_cand, dim, dtype, mma).total;
+}
+
+int ffr_filter_ex(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype,
+                  const float* ref_norm, const float* cand_norm, int metric, float thr, int64_t ref_index_base,
+                  uint8_t* keep, int32_t* best_idx, float* best_val, float band_tol, int32_t* band_count,
+                  int64_t* band_rows, int64_t band_cap, int flags, void* workspace, size_t ws_bytes,
+                  ffr_stream_t stream) {
+    (void)ref_norm; (void)cand_norm;     // cosine on pre-normalised fp16 rows needs no norms
+    int rc = check_common(ref, n_ref, cand, n_cand, dim, dtype, metric, keep, best_idx);
+    if (rc != FFR_OK) return rc;
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    return filter_core(ref, nullptr, n_ref, cand, n_cand, dim, dtype, metric, thr, ref_index_base, keep, best_idx,
+                       best_val, band_tol, band_count, band_rows, band_cap, flags, workspace, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ffr_filter(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype,
+               const float* ref_norm, const float* cand_norm, int metric, float thr, int64_t ref_index_base,
+               uint8_t* keep, int32_t* best_idx, float* best_val, void* workspace, size_t ws_bytes,
+               ffr_stream_t stream) {
+    return ffr_filter_ex(ref, n_ref, cand, n_cand, dim, dtype, ref_norm, cand_norm, metric, thr, ref_index_base, keep,
+                         best_idx, best_val, 0.f, nullptr, nullptr, 0, 0, workspace, ws_bytes, stream);
+}
+
+int ffr_filter_stats(const void* workspace, int64_t out[4], ffr_stream_t stream) {
+    if (workspace == nullptr || out == nullptr) { set_error("filter_stats: null argument"); return FFR_ERR_INVALID; }
+    WsHeader h;
+    FFR_CUDA_TRY(cudaMemcpyAsync(&h, workspace, sizeof(h), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    FFR_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    out[0] = h.recheck_count; out[1] = h.full_count;
+    out[2] = g_last.ws == workspace ? g_last.path : -1;
+    out[3] = g_last.ws == workspace ? g_last.launches : -1;
+    return FFR_OK;
+}
+
+int ffr_ref_mean_and_thres(const float* ref_feat, int32_t n_ref, int32_t dim, float* mean, float* thres,
+                           ffr_stream_t stream) {
+    if (ref_feat == nullptr || mean == nullptr || thres == nullptr) { set_error("ref_mean_and_thres: null argument"); return FFR_ERR_INVALID; }
+    if (n_ref <= 0 || n_ref > 4096 || dim <= 0 || dim > 8192) { set_error("ref_mean_and_thres: need 0 < n_ref <= 4096, 0 < dim <= 8192"); return FFR_ERR_INVALID; }
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    return launch_ref_stats(ref_feat, n_ref, dim, mean, thres, static_cast<cudaStream_t>(stream));
+}
+
+// test hook (not in the public header): tcgen05 kernel on fp16 rows, dumping every score
+int ffr_debug_mma_scores(const void* ref16, int64_t n_ref, const void* cand16, int64_t n_cand, int32_t dim_pad,
+                         float thr, uint8_t* keep, int32_t* idx, float* val, float* scores, void* workspace,
+                         size_t ws_bytes, ffr_stream_t stream) {
+    const size_t need = 256 + static_cast<size_t>(n_cand) * sizeof(RecheckRec);
+    if (workspace == nullptr || ws_bytes < need) { set_error("debug_mma_scores: workspace needs %zu bytes", need); return FFR_ERR_WORKSPACE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FFR_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256, s));
+    return launch_filter_mma_debug(static_cast<const __half*>(ref16), n_ref, static_cast<const __half*>(cand16), n_cand,
+                                   dim_pad, thr, g_delta, keep, idx, val, static_cast<WsHeader*>(workspace),
+                                   reinterpret_cast<RecheckRec*>(static_cast<uint8_t*>(workspace) + 256), n_cand, scores, s);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer pipeline
+struct ffr_ctx {
+    int device;
+    int64_t max_ref, chunk;
+    int32_t max_dim;
+    cudaStream_t s_copy, s_comp;
+    cudaEvent_t ev_h2d[2], ev_done[2];
+    float* d_ref;
+    __half* d_ref16;
+    float* d_cand[2];
+    uint8_t* d_keep[2];
+    int32_t* d_idx[2];
+    float* d_val[2];
+    void* ws[2];
+    size_t ws_bytes;
+    int64_t launches;
+};
+
+extern "C" {
+
+void ffr_ctx_destroy(ffr_ctx* c) {
+    if (c == nullptr) return;
+    cudaSetDevice(c->device);
+    if (c->s_comp) cudaStreamSynchronize(c->s_comp);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    cudaFree(c->d_ref); cudaFree(c->d_ref16);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_cand[i]); cudaFree(c->d_keep[i]); cudaFree(c->d_idx[i]); cudaFree(c->d_val[i]); cudaFree(c->ws[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    delete c;
+}
+
+int ffr_ctx_create(int device, int64_t max_ref, int64_t chunk_cand, int32_t max_dim, ffr_ctx** out) {
+    if (out == nullptr || max_ref <= 0 || chunk_cand <= 0 || max_dim <= 0) { set_error("ctx_create: bad argument"); return FFR_ERR_INVALID; }
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    ffr_ctx* c = new (std::nothrow) ffr_ctx();
+    if (c == nullptr) { set_error("out of host memory"); return FFR_ERR_INVALID; }
+    memset(c, 0, sizeof(*c));
+    c->device = device; c->max_ref = max_ref; c->chunk = chunk_cand; c->max_dim = max_dim;
+#define FFR_CTX_TRY(expr)                                                                          \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int _rc = cuda_fail(_e, #expr); ffr_ctx_destroy(c); return _rc; } } while (0)
+    FFR_CTX_TRY(cudaSetDevice(device));
+    FFR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    FFR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    const size_t ld = static_cast<size_t>(ffr_padded_dim(max_dim));
+    FFR_CTX_TRY(cudaMalloc(&c->d_ref, static_cast<size_t>(max_ref) * max_dim * sizeof(float)));
+    FFR_CTX_TRY(cudaMalloc(&c->d_ref16, static_cast<size_t>(max_ref) * ld * 2));
+    c->ws_bytes = ffr_filter_workspace_bytes(1, chunk_cand, max_dim <= 512 ? max_dim : 512, FFR_DTYPE_F32, FFR_METRIC_COSINE);
+    if (c->ws_bytes < 4096) c->ws_bytes = 4096;
+    for (int i = 0; i < 2; ++i) {
+        FFR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        FFR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        FFR_CTX_TRY(cudaMalloc(&c->d_cand[i], static_cast<size_t>(chunk_cand) * max_dim * sizeof(float)));
+        FFR_CTX_TRY(cudaMalloc(&c->d_keep[i], static_cast<size_t>(chunk_cand)));
+        FFR_CTX_TRY(cudaMalloc(&c->d_idx[i], static_cast<size_t>(chunk_cand) * sizeof(int32_t)));
+        FFR_CTX_TRY(cudaMalloc(&c->d_val[i], static_cast<size_t>(chunk_cand) * sizeof(float)));
+        FFR_CTX_TRY(cudaMalloc(&c->ws[i], c->ws_bytes));
+    }
+#undef FFR_CTX_TRY
+    *out = c;
+    return FFR_OK;
+}
+
+int ffr_ctx_filter_host(ffr_ctx* c, const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
+                        int metric, float thr, int64_t ref_index_base, uint8_t* keep, int32_t* best_idx,
+                        float* best_val, int flags) {
+    if (c == nullptr) { set_error("ctx is null"); return FFR_ERR_INVALID; }
+    int rc = check_common(ref, n_ref, cand, n_cand, dim, FFR_DTYPE_F32, metric, keep, best_idx);
+    if (rc != FFR_OK) return rc;
+    if (n_ref > c->max_ref || dim > c->max_dim) { set_error("ctx sized for n_ref <= %lld, dim <= %d", (long long)c->max_ref, c->max_dim); return FFR_ERR_INVALID; }
+    FFR_CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t l0 = ffr_launch_count();
+    const bool mma = mma_eligible(n_ref, dim, metric, flags);
+    FFR_CUDA_TRY(cudaMemcpyAsync(c->d_ref, ref, static_cast<size_t>(n_ref) * dim * sizeof(float), cudaMemcpyHostToDevice, c->s_comp));
+    const __half* ref16 = nullptr;
+    if (mma) {      // references are normalised / converted once, not per chunk
+        rc = launch_l2norm(c->d_ref, n_ref, dim, c->d_ref16, ffr_padded_dim(dim), nullptr, nullptr, c->s_comp);
+        if (rc != FFR_OK) return rc;
+        ref16 = c->d_ref16;
+    }
+    int64_t i = 0;
+    for (int64_t off = 0; off < n_cand; off += c->chunk, ++i) {
+        const int b = static_cast<int>(i & 1);
+        const int64_t m = (n_cand - off) < c->chunk ? (n_cand - off) : c->chunk;
+        if (i >= 2) FFR_CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[b], 0));     // buffer b free again
+        FFR_CUDA_TRY(cudaMemcpyAsync(c->d_cand[b], cand + off * dim, static_cast<size_t>(m) * dim * sizeof(float),
+                                     cudaMemcpyHostToDevice, c->s_copy));
+        FFR_CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->s_copy));
+        FFR_CUDA_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_h2d[b], 0));
+        rc = filter_core(c->d_ref, ref16, n_ref, c->d_cand[b], m, dim, FFR_DTYPE_F32, metric, thr, ref_index_base,
+                         c->d_keep[b], c->d_idx[b], c->d_val[b], 0.f, nullptr, nullptr, 0, flags, c->ws[b], c->ws_bytes,
+                         c->s_comp);
+        if (rc != FFR_OK) return rc;
+        FFR_CUDA_TRY(cudaMemcpyAsync(keep + off, c->d_keep[b], static_cast<size_t>(m), cudaMemcpyDeviceToHost, c->s_comp));
+        FFR_CUDA_TRY(cudaMemcpyAsync(best_idx + off, c->d_idx[b], static_cast<size_t>(m) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_comp));
+        if (best_val != nullptr)
+            FFR_CUDA_TRY(cudaMemcpyAsync(best_val + off, c->d_val[b], static_cast<size_t>(m) * sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
+        FFR_CUDA_TRY(cudaEventRecord(c->ev_done[b], c->s_comp));
+    }
+    FFR_CUDA_TRY(cudaStreamSynchronize(c->s_comp));
+    c->launches += ffr_launch_count() - l0;
+    return FFR_OK;
+}
+
+int64_t ffr_ctx_launch_count(const ffr_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL gather (dlopen)
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+typedef int (*pfn_get_uid)(nccl_uid*);
+typedef int (*pfn_init_rank)(nccl_comm_t*, int, nccl_uid, int);
+typedef int (*pfn_allgather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
+typedef int (*pfn_destroy)(nccl_comm_t);
+typedef const char* (*pfn_errstr)(int);
+struct NcclApi {
+    void* h = nullptr;
+    pfn_get_uid get_uid = nullptr;
+    pfn_init_rank init_rank = nullptr;
+    pfn_allgather allgather = nullptr;
+    pfn_destroy destroy = nullptr;
+    pfn_errstr errstr = nullptr;
+    bool ok = false;
+} g_nccl;
+
+int nccl_load() {
+    if (g_nccl.ok) return FFR_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return FFR_ERR_NCCL; }
+    g_nccl.get_uid = reinterpret_cast<pfn_get_uid>(dlsym(g_nccl.h, "ncclGetUniqueId"));
+    g_nccl.init_rank = reinterpret_cast<pfn_init_rank>(dlsym(g_nccl.h, "ncclCommInitRank"));
+    g_nccl.allgather = reinterpret_cast<pfn_allgather>(dlsym(g_nccl.h, "ncclAllGather"));
+    g_nccl.destroy = reinterpret_cast<pfn_destroy>(dlsym(g_nccl.h, "ncclCommDestroy"));
+    g_nccl.errstr = reinterpret_cast<pfn_errstr>(dlsym(g_nccl.h, "ncclGetErrorString"));
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allgather || !g_nccl.destroy) {
+        set_error("libnccl is missing expected symbols");
+        return FFR_ERR_NCCL;
+    }
+    g_nccl.ok = true;
+    return FFR_OK;
+}
+int nccl_fail(int code, const char* what) {
+    set_error("NCCL error %d (%s) at %s", code, g_nccl.errstr ? g_nccl.errstr(code) : "?", what);
+    return FFR_ERR_NCCL;
+}
+}  // namespace
+
+struct ffr_comm {
+    nccl_comm_t comm;
+    int nranks, rank, device;
+};
+
+extern "C" {
+
+int ffr_nccl_unique_id(void* id128) {
+    if (id128 == nullptr) { set_error("unique_id: null"); return FFR_ERR_INVALID; }
+    int rc = nccl_load();
+    if (rc != FFR_OK) return rc;
+    nccl_uid uid;
+    const int e = g_nccl.get_uid(&uid);
+    if (e != 0) return nccl_fail(e, "ncclGetUniqueId");
+    memcpy(id128, &uid, sizeof(uid));
+    return FFR_OK;
+}
+
+int ffr_comm_create(const void* id128, int nranks, int rank, int device, ffr_comm** out) {
+    if (id128 == nullptr || out == nullptr || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("comm_create: bad argument"); return FFR_ERR_INVALID; }
+    int rc = nccl_load();
+    if (rc != FFR_OK) return rc;
+    FFR_CUDA_TRY(cudaSetDevice(device));
+    nccl_uid uid;
+    memcpy(&uid, id128, sizeof(uid));
+    ffr_comm* c = new (std::nothrow) ffr_comm();
+    if (c == nullptr) { set_error("out of host memory"); return FFR_ERR_INVALID; }
+    c->nranks = nranks; c->rank = rank; c->device = device; c->comm = nullptr;
+    const int e = g_nccl.init_rank(&c->comm, nranks, uid, rank);
+    if (e != 0) { delete c; return nccl_fail(e, "ncclCommInitRank"); }
+    *out = c;
+    return FFR_OK;
+}
+
+void ffr_comm_destroy(ffr_comm* c) {
+    if (c == nullptr) return;
+    if (c->comm && g_nccl.ok) g_nccl.destroy(c->comm);
+    delete c;
+}
+
+size_t ffr_allgather_workspace_bytes(int nranks, int64_t m_local) {
+    if (nranks <= 0 || m_local < 0) return 0;
+    const size_t m_pad = (static_cast<size_t>(m_local) + 15) / 16 * 16;
+    return (static_cast<size_t>(nranks) + 1) * m_pad * 5 + 256;
+}
+
+int ffr_allgather_results(ffr_comm* c, const uint8_t* keep_local, const int32_t* idx_local, int64_t m_local,
+                          uint8_t* keep_all, int32_t* idx_all, void* workspace, size_t ws_bytes, ffr_stream_t stream) {
+    if (c == nullptr || keep_local == nullptr || idx_local == nullptr || keep_all == nullptr || idx_all == nullptr) { set_error("allgather: null argument"); return FFR_ERR_INVALID; }
+    if (m_local < 0) { set_error("allgather: m_local < 0"); return FFR_ERR_INVALID; }
+    if (m_local == 0) return FFR_OK;
+    const size_t need = ffr_allgather_workspace_bytes(c->nranks, m_local);
+    if (workspace == nullptr || ws_bytes < need) { set_error("allgather: workspace needs %zu bytes", need); return FFR_ERR_WORKSPACE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t m_pad = (m_local + 15) / 16 * 16;
+    uint8_t* send = static_cast<uint8_t*>(workspace);
+    uint8_t* recv = send + static_cast<size_t>(m_pad) * 5;
+    int rc = launch_pack_results(keep_local, idx_local, m_local, m_pad, send, s);
+    if (rc != FFR_OK) return rc;
+    const int e = g_nccl.allgather(send, recv, static_cast<size_t>(m_pad) * 5, /*ncclUint8*/ 1, c->comm, s);
+    if (e != 0) return nccl_fail(e, "ncclAllGather");
+    return launch_unpack_results(recv, m_local, m_pad, c->nranks, keep_all, idx_all, s);
+}
+
+}  // extern "C"
