@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference's golden outputs.
+
+Bars: similarities within 1e-3 absolute of the fp32 oracle; keep mask and best index exact,
+except (a) rows whose fp64 best lies within the tolerance band of the threshold (listed) and (b) rows whose two
+leading fp64 scores differ by less than fp32 summation noise (1e-6), where "the fp32 argmax" is itself
+ill-defined.  Integer outputs are otherwise compared bit-exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+VAL_TOL = 1e-3          # north_star: similarities within 1e-3 absolute
+TIE_EPS = 1e-6          # fp32 summation-order noise on a unit-norm dot product
+
+
+@pytest.fixture(scope="module")
+def ops(ffr_lib, cuda_dev):
+    from face_detection_and_recognition_b200 import ops as _ops
+    return _ops
+
+
+def _top2_gap64(ref, cand):
+    r = ref.astype(np.float64)
+    c = cand.astype(np.float64)
+    r /= np.linalg.norm(r, axis=1, keepdims=True)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    s = r @ c.T
+    if s.shape[0] == 1:
+        return np.full(s.shape[1], np.inf), s[0]
+    part = np.partition(s, -2, axis=0)
+    return part[-1] - part[-2], part[-1]
+
+
+def _check_cosine(ops, ref, cand, thr, flags=0, band_tol=1e-3):
+    dev = torch.device("cuda:0")
+    res = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev), thr, metric="cosine",
+                          band_tol=band_tol, flags=flags, want_stats=True)
+    torch.cuda.synchronize()
+    keep, idx, val = res.keep.cpu().numpy(), res.best_idx.cpu().numpy(), res.best_val.cpu().numpy()
+    ko, io, so = oracle.filter_cosine(ref, cand, thr)
+    gap, best64 = _top2_gap64(ref, cand)
+    assert np.max(np.abs(val - so)) <= VAL_TOL, f"max |sim - oracle| = {np.max(np.abs(val - so))}"
+    unamb = gap > TIE_EPS
+    bad_idx = np.flatnonzero((idx != io) & unamb)
+    assert bad_idx.size == 0, (f"{bad_idx.size} index mismatches outside fp32-tie rows, e.g. row {bad_idx[:5]} "
+                               f"got {idx[bad_idx[:5]]} want {io[bad_idx[:5]]} gap {gap[bad_idx[:5]]} stats {res.stats}")
+    band = oracle.tolerance_band(best64, thr, TIE_EPS)
+    outside = np.ones(len(keep), bool)
+    outside[band] = False
+    bad_keep = np.flatnonzero((keep != ko) & outside)
+    assert bad_keep.size == 0, f"{bad_keep.size} keep mismatches outside the band, e.g. {bad_keep[:5]} {best64[bad_keep[:5]]}"
+    # the listed band must contain every row whose fp64 best is within band_tol - noise of thr
+    if band_tol is not None:
+        listed = set(res.band_rows.cpu().numpy().tolist())
+        must = set(np.flatnonzero(np.abs(best64 - thr) <= band_tol - 1e-5).tolist())
+        may = set(np.flatnonzero(np.abs(best64 - thr) <= band_tol + 1e-5).tolist())
+        assert must <= listed <= may, (len(must - listed), len(listed - may))
+    return res
+
+
+# ---------------------------------------------------------------- K1
+@pytest.mark.parametrize("rows,dim", [(1, 128), (37, 128), (1000, 512), (333, 256), (64, 384), (7, 1024), (19, 100),
+                                      (5, 3), (4097, 128)])
+def test_l2norm_rows(ops, rows, dim):
+    rng = np.random.default_rng(rows * 1000 + dim)
+    x = (rng.standard_normal((rows, dim)) * rng.uniform(0.01, 30)).astype(np.float32)
+    out = ops.l2norm_rows(torch.from_numpy(x).cuda(), want_f16=True, want_f32=True, want_norms=True)
+    torch.cuda.synchronize()
+    y = oracle.l2_norm(x)
+    np.testing.assert_allclose(out["f32"].cpu().numpy(), y, rtol=4e-7, atol=1e-9)
+    np.testing.assert_allclose(out["norms"].cpu().numpy(), oracle.row_norms(x), rtol=4e-7)
+    y16 = out["f16"].cpu().numpy()
+    ld = (dim + 63) // 64 * 64
+    assert y16.shape == (rows, ld) and y16.dtype == np.float16
+    # fp16 copy = round-to-nearest of the fp32 result (allow 1 fp16 ulp where the fp32 values differ by an ulp)
+    np.testing.assert_allclose(y16[:, :dim].astype(np.float32), y, rtol=1e-3, atol=1e-7)
+    assert np.all(y16[:, dim:] == 0)
+
+
+def test_l2norm_golden(ops, golden_dir):
+    """K1 against the reference's own l2_norm outputs (mobile_facenet.py:30-33)."""
+    g = np.load(os.path.join(golden_dir, "l2norm_ref.npz"))
+    for k in "abcd":
+        out = ops.l2norm_rows(torch.from_numpy(g[f"{k}_x"]).cuda())
+        np.testing.assert_allclose(out["f32"].cpu().numpy(), g[f"{k}_y"], rtol=4e-7, atol=1e-9)
+
+
+# ---------------------------------------------------------------- K5 + K2s against the reference's main()
+@pytest.mark.parametrize("name", ["ref_main_facenetlike.npz", "ref_main_mobilefacenet.npz"])
+def test_reference_main_golden(ops, golden_dir, name):
+    """BASELINE configs[0]: mean vector, threshold and every clean/unclean decision the reference's main() took
+    on the bundled faces (filter_faces_using_reference.py:85-99, :186-189) are reproduced on the GPU."""
+    g = np.load(os.path.join(golden_dir, name))
+    for c in range(int(g["n_classes"])):
+        ref_feat = torch.from_numpy(g[f"c{c}_ref_feat"]).cuda()
+        mean, thres = ops.ref_mean_and_thres(ref_feat)
+        np.testing.assert_allclose(mean.cpu().numpy(), g[f"c{c}_mu"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(float(thres), float(g[f"c{c}_thres"]), rtol=1e-6)
+        # decisions with the reference's own (mu, thres)
+        cand = g[f"c{c}_cand"]
+        res = ops.face_filter(torch.from_numpy(g[f"c{c}_mu"]).cuda(), torch.from_numpy(cand).cuda(),
+                              float(g[f"c{c}_thres"]), metric="euclid")
+        keep = res.keep.cpu().numpy()
+        d64 = np.linalg.norm(cand.astype(np.float64) - g[f"c{c}_mu"].astype(np.float64), axis=1)
+        noise = np.abs(d64 - float(g[f"c{c}_thres"])) < 1e-6 * max(1.0, float(g[f"c{c}_thres"]))
+        assert np.array_equal(keep[~noise], g[f"c{c}_keep"][~noise]), np.flatnonzero(keep != g[f"c{c}_keep"])
+        assert noise.sum() <= 2
+        np.testing.assert_allclose(res.best_val.cpu().numpy(), d64, rtol=2e-6, atol=1e-6)
+        assert np.all(res.best_idx.cpu().numpy() == 0)
+        # and end to end with the GPU's own (mu, thres)
+        res2 = ops.face_filter(mean, torch.from_numpy(cand).cuda(), float(thres), metric="euclid")
+        k2 = res2.keep.cpu().numpy()
+        assert np.array_equal(k2[~noise], g[f"c{c}_keep"][~noise])
+
+
+# ---------------------------------------------------------------- K2s (exact fp32 CUDA-core path)
+@pytest.mark.parametrize("n_ref,n_cand,dim,metric", [
+    (1, 1000, 128, "euclid"), (1, 777, 512, "euclid"), (1, 50, 100, "euclid"), (3, 500, 128, "euclid"),
+    (8, 300, 128, "cosine"), (2, 301, 512, "cosine"), (5, 64, 256, "cosine"), (40, 200, 128, "euclid"),
+    (33, 100, 36, "cosine"), (4, 129, 1024, "euclid"), (6, 10, 2048, "cosine")])
+def test_filter_fp32_small(ops, n_ref, n_cand, dim, metric):
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref + n_cand + dim, unit_norm=(metric == "cosine"))
+    from face_detection_and_recognition_b200.ops import FLAG_FORCE_FP32
+    if metric == "euclid":
+        thr = float(np.median(oracle.filter_euclid(ref, cand, 0)[2]))
+        ko, io, so = oracle.filter_euclid(ref, cand, thr)
+    else:
+        thr = 0.5
+        ko, io, so = oracle.filter_cosine(ref, cand, thr)
+    res = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), thr, metric=metric,
+                          flags=FLAG_FORCE_FP32, want_stats=True)
+    assert res.stats["path"] == "fp32"
+    keep, idx, val = res.keep.cpu().numpy(), res.best_idx.cpu().numpy(), res.best_val.cpu().numpy()
+    np.testing.assert_allclose(val, so, rtol=3e-6, atol=3e-6)
+    near = np.abs(so - thr) < 1e-5 * max(1.0, abs(thr))
+    assert np.array_equal(keep[~near], ko[~near])
+    assert np.mean(idx == io) > 0.995            # fp32 near-ties only
+    assert np.all(np.abs(val - so)[idx != io] < 1e-5)
+
+
+def test_filter_fp32_index_base_and_empty(ops):
+    ref, cand = oracle.make_synthetic(4, 10, 128, seed=1)
+    r = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, ref_index_base=1000)
+    _, io, _ = oracle.filter_cosine(ref, cand, 0.5)
+    assert np.array_equal(r.best_idx.cpu().numpy(), io + 1000)
+    e = ops.face_filter(torch.from_numpy(ref).cuda(), torch.empty((0, 128), device="cuda"), 0.5)
+    assert e.keep.numel() == 0 and e.best_idx.numel() == 0
+
+
+# ---------------------------------------------------------------- K2 raw scores (validates TMA/UMMA descriptors)
+@pytest.mark.parametrize("n_ref,n_cand,dim", [(256, 128, 64), (256, 128, 128), (512, 256, 512), (100, 77, 128),
+                                              (300, 130, 256), (1000, 333, 192), (17, 5, 64)])
+def test_mma_raw_scores(ffr_lib, ops, n_ref, n_cand, dim):
+    """Every accumulator element the tcgen05 kernel produces == fp32 dot of the same fp16-rounded rows."""
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=11)
+    r16 = ops.l2norm_rows(torch.from_numpy(ref).cuda(), want_f16=True, want_f32=False)["f16"]
+    c16 = ops.l2norm_rows(torch.from_numpy(cand).cuda(), want_f16=True, want_f32=False)["f16"]
+    ld = r16.shape[1]
+    scores = torch.full((n_cand, n_ref), float("nan"), device="cuda")
+    keep = torch.empty(n_cand, dtype=torch.uint8, device="cuda")
+    idx = torch.empty(n_cand, dtype=torch.int32, device="cuda")
+    val = torch.empty(n_cand, dtype=torch.float32, device="cuda")
+    ws = torch.zeros(256 + 16 * n_cand + 256, dtype=torch.uint8, device="cuda")
+    from face_detection_and_recognition_b200._lib import check
+    check(ffr_lib.ffr_debug_mma_scores(r16.data_ptr(), n_ref, c16.data_ptr(), n_cand, ld, 0.5, keep.data_ptr(),
+                                       idx.data_ptr(), val.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = (c16.float() @ r16.float().T).cpu().numpy()
+    got = scores.cpu().numpy()
+    assert not np.isnan(got).any(), f"{np.isnan(got).sum()} score elements never written"
+    err = np.abs(got - want)
+    assert err.max() < 2e-5, (f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}; "
+                              f"per-column-block max {[float(err[:, i:i + 32].max()) for i in range(0, min(n_ref, 256), 32)]}")
+    np.testing.assert_allclose(val.cpu().numpy(), want.max(axis=1), atol=2e-5)
+    assert np.mean(idx.cpu().numpy() == want.argmax(axis=1)) > 0.99
+
+
+# ---------------------------------------------------------------- K1+K2+K3 end to end
+@pytest.mark.parametrize("n_ref,n_cand,dim", [
+    (9, 100, 128), (255, 1000, 128), (256, 1000, 128), (257, 1000, 128), (1000, 5000, 128), (300, 129, 512),
+    (2000, 3000, 512), (513, 1, 256), (64, 4000, 64), (700, 900, 200), (1111, 2049, 384)])
+def test_filter_mma_vs_oracle(ops, n_ref, n_cand, dim):
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref * 7 + dim, n_adversarial=min(200, n_cand // 4),
+                                      n_dup_refs=min(32, n_ref // 4))
+    res = _check_cosine(ops, ref, cand, 0.5)
+    assert res.stats["path"] == "tcgen05"
+
+
+def test_filter_mma_unnormalised_inputs(ops):
+    """Raw (un-normalised) embeddings: cosine is scale invariant, K1 normalises internally."""
+    ref, cand = oracle.make_synthetic(600, 2500, 128, seed=77, unit_norm=False, n_adversarial=100, n_dup_refs=8)
+    _check_cosine(ops, ref, cand, 0.5)
+
+
+def test_filter_mma_exact_ties_pick_first(ops):
+    """Duplicated references give exactly equal scores: best_idx must be the FIRST occurrence (np.argmax)."""
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((40, 128)).astype(np.float32)
+    ref = np.concatenate([base, base, base], axis=0)              # 120 refs, every one appears 3 times
+    cand = (base[rng.integers(0, 40, 900)] + 0.3 * rng.standard_normal((900, 128))).astype(np.float32)
+    dev = torch.device("cuda:0")
+    from face_detection_and_recognition_b200.ops import FLAG_FORCE_MMA
+    res = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev), 0.5, flags=FLAG_FORCE_MMA,
+                          want_stats=True)
+    idx = res.best_idx.cpu().numpy()
+    assert np.all(idx < 40), f"{np.sum(idx >= 40)} rows picked a later duplicate"
+    _, io, _ = oracle.filter_cosine(base, cand, 0.5)
+    gap, _ = _top2_gap64(base, cand)
+    assert np.array_equal(idx[gap > TIE_EPS], io[gap > TIE_EPS])
+    assert res.stats["full_rescans"] > 0                          # triple ties force the full fp32 rescan
+
+
+def test_filter_mma_config2_full(ops):
+    """BASELINE configs[1] in full: 1k references x 100k candidates x 128-d, threshold 0.5."""
+    ref, cand = oracle.make_synthetic(1000, 100_000, 128, seed=42, n_adversarial=1000, n_dup_refs=100)
+    res = _check_cosine(ops, ref, cand, 0.5)
+    assert 0.3 < res.keep.float().mean().item() < 0.7
+
+
+def test_filter_mma_f16_inputs(ops):
+    """Pre-normalised fp16 rows in (FFR_DTYPE_F16): no fp32 re-check possible, values still within 1e-3."""
+    ref, cand = oracle.make_synthetic(500, 2000, 256, seed=8)
+    r16 = ops.l2norm_rows(torch.from_numpy(ref).cuda(), want_f16=True, want_f32=False)["f16"]
+    c16 = ops.l2norm_rows(torch.from_numpy(cand).cuda(), want_f16=True, want_f32=False)["f16"]
+    res = ops.face_filter(r16, c16, 0.5)
+    ko, io, so = oracle.filter_cosine(ref, cand, 0.5)
+    assert np.max(np.abs(res.best_val.cpu().numpy() - so)) < VAL_TOL
+    assert np.mean(res.best_idx.cpu().numpy() == io) > 0.99
+    far = np.abs(so - 0.5) > VAL_TOL
+    assert np.array_equal(res.keep.cpu().numpy()[far], ko[far])
+
+
+def test_host_filter_matches_device_path(ops):
+    ref, cand = oracle.make_synthetic(300, 10_000, 128, seed=21)
+    hf = ops.HostFilter(device=0, max_ref=1024, chunk_cand=3000, max_dim=128)
+    keep, idx, val = hf(ref, cand, 0.5)
+    res = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5)
+    assert np.array_equal(keep, res.keep.cpu().numpy())
+    assert np.array_equal(idx, res.best_idx.cpu().numpy())
+    np.testing.assert_allclose(val, res.best_val.cpu().numpy(), atol=1e-6)
+    assert hf.launches > 0
+    # euclid, one mean vector (the reference's literal mode) through the host entry point
+    mu = ref[:1] * 3.0
+    keep_e, idx_e, val_e = hf(mu, cand * 3.0, 4.0, metric="euclid")
+    ko, io, so = oracle.filter_euclid(mu, cand * 3.0, 4.0)
+    near = np.abs(so - 4.0) < 1e-5
+    assert np.array_equal(keep_e[~near], ko[~near])
+    hf.close()
+
+
+def test_errors_are_loud(ffr_lib, ops):
+    from face_detection_and_recognition_b200._lib import FfrError
+    ref = torch.randn(16, 128, device="cuda")
+    cand = torch.randn(32, 128, device="cuda")
+    with pytest.raises(TypeError):
+        ops.face_filter(ref.cpu(), cand, 0.5)
+    with pytest.raises(ValueError):
+        ops.face_filter(ref, cand[:, :64], 0.5)
+    with pytest.raises(FfrError):                                  # workspace too small is reported, not ignored
+        from face_detection_and_recognition_b200._lib import check
+        keep = torch.empty(32, dtype=torch.uint8, device="cuda")
+        idx = torch.empty(32, dtype=torch.int32, device="cuda")
+        check(ffr_lib.ffr_filter(ref.data_ptr(), 16, cand.data_ptr(), 32, 128, 0, None, None, 0, 0.5, 0,
+                                 keep.data_ptr(), idx.data_ptr(), None, None, 0, None))
