@@ -20,6 +20,8 @@ std::atomic<int64_t> g_launches{0};
 float g_delta = 4e-4f;       // recheck window in cosine units, see DESIGN.md §4 (fp16 operand rounding)
 struct LastCall { const void* ws; int path; int launches; };
 thread_local LastCall g_last = {nullptr, 0, 0};
+// profiling hook: CUDA events recorded on the launch stream right before / after the tcgen05 kernel
+thread_local cudaEvent_t g_ev_k2_begin = nullptr, g_ev_k2_end = nullptr;
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -53,7 +55,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t hdr, ref16, cand16, recs, total;
+    size_t hdr, ref16, cand16, recs, full_rows, full_keys, full_ctr, total;
     bool mma;
 };
 
@@ -74,7 +76,10 @@ WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool m
         const size_t ld = static_cast<size_t>(ffr_padded_dim(dim));
         L.ref16 = off;  if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_ref) * ld * 2, 256);
         L.cand16 = off; if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_cand) * ld * 2, 256);
-        L.recs = off;   off += align_up(static_cast<size_t>(n_cand) * sizeof(RecheckRec), 256);
+        L.recs = off;      off += align_up(static_cast<size_t>(n_cand) * sizeof(RecheckRec), 256);
+        L.full_rows = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(int32_t), 256);
+        L.full_keys = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(unsigned long long), 256);
+        L.full_ctr = off;  off += align_up((static_cast<size_t>(n_cand) / kFullGroup + 1) * sizeof(int32_t), 256);
     }
     L.total = off;
     return L;
@@ -151,17 +156,26 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         cand16 = static_cast<const __half*>(cand);
     }
     const bool recheck = (dtype == FFR_DTYPE_F32) && !(flags & FFR_FLAG_NO_RECHECK);
-    g_last.launches = launches + 1 + (recheck ? 1 : 0);
-    RecheckRec* recs = reinterpret_cast<RecheckRec*>(ws + L.recs);
+    g_last.launches = launches + 1 + (recheck ? 2 : 0);
+    RecheckLists lists;
+    lists.hdr = hdr;
+    lists.recs = reinterpret_cast<RecheckRec*>(ws + L.recs);
+    lists.rec_cap = n_cand;
+    lists.full_rows = reinterpret_cast<int32_t*>(ws + L.full_rows);
+    lists.full_keys = reinterpret_cast<unsigned long long*>(ws + L.full_keys);
+    lists.full_ctr = reinterpret_cast<int32_t*>(ws + L.full_ctr);
+    lists.full_cap = n_cand;
     const float delta = g_delta;
     float thr_band = delta;
     if (band_count != nullptr && band_tol + delta > thr_band) thr_band = band_tol + delta;
+    if (g_ev_k2_begin != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_begin, s));
     rc = launch_filter_mma(ref16, n_ref, cand16, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
-                           best_val, hdr, recs, n_cand, recheck ? 0 : 1, s);
+                           best_val, lists, recheck ? 0 : 1, s);
     if (rc != FFR_OK) return rc;
+    if (g_ev_k2_end != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_end, s));
     if (recheck) {
         rc = launch_recheck(static_cast<const float*>(ref), n_ref, static_cast<const float*>(cand), n_cand, dim, nullptr,
-                            nullptr, thr, ref_index_base, keep, best_idx, best_val, hdr, recs, n_cand, band_tol,
+                            nullptr, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol,
                             band_count, band_rows, band_cap, s);
         if (rc != FFR_OK) return rc;
     }
@@ -191,6 +205,11 @@ int64_t ffr_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 // not in the public header: tuning / test hooks
 void ffr_set_recheck_delta(float d) { g_delta = d; }
+// cudaEvent_t pair recorded around the next tcgen05 kernel launches of this thread (NULL, NULL to disable)
+void ffr_debug_set_k2_events(void* begin, void* end) {
+    g_ev_k2_begin = static_cast<cudaEvent_t>(begin);
+    g_ev_k2_end = static_cast<cudaEvent_t>(end);
+}
 float ffr_get_recheck_delta(void) { return g_delta; }
 
 int ffr_l2norm_rows_f32(const float* x, int64_t rows, int32_t dim, void* y_f16, int32_t y_f16_ld, float* y_f32,
@@ -255,13 +274,23 @@ int ffr_ref_mean_and_thres(const float* ref_feat, int32_t n_ref, int32_t dim, fl
 int ffr_debug_mma_scores(const void* ref16, int64_t n_ref, const void* cand16, int64_t n_cand, int32_t dim_pad,
                          float thr, uint8_t* keep, int32_t* idx, float* val, float* scores, void* workspace,
                          size_t ws_bytes, ffr_stream_t stream) {
-    const size_t need = 256 + static_cast<size_t>(n_cand) * sizeof(RecheckRec);
+    const size_t n = static_cast<size_t>(n_cand);
+    const size_t need = 256 + align_up(n * sizeof(RecheckRec), 256) + align_up(n * 4, 256) + align_up(n * 8, 256) +
+                        align_up((n / kFullGroup + 1) * 4, 256);
     if (workspace == nullptr || ws_bytes < need) { set_error("debug_mma_scores: workspace needs %zu bytes", need); return FFR_ERR_WORKSPACE; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     FFR_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256, s));
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    RecheckLists lists;
+    lists.hdr = reinterpret_cast<WsHeader*>(ws);
+    size_t off = 256;
+    lists.recs = reinterpret_cast<RecheckRec*>(ws + off); off += align_up(n * sizeof(RecheckRec), 256);
+    lists.full_rows = reinterpret_cast<int32_t*>(ws + off); off += align_up(n * 4, 256);
+    lists.full_keys = reinterpret_cast<unsigned long long*>(ws + off); off += align_up(n * 8, 256);
+    lists.full_ctr = reinterpret_cast<int32_t*>(ws + off);
+    lists.rec_cap = lists.full_cap = n_cand;
     return launch_filter_mma_debug(static_cast<const __half*>(ref16), n_ref, static_cast<const __half*>(cand16), n_cand,
-                                   dim_pad, thr, g_delta, keep, idx, val, static_cast<WsHeader*>(workspace),
-                                   reinterpret_cast<RecheckRec*>(static_cast<uint8_t*>(workspace) + 256), n_cand, scores, s);
+                                   dim_pad, thr, g_delta, keep, idx, val, lists, scores, s);
 }
 
 }  // extern "C"

@@ -39,6 +39,20 @@ struct RecheckRec {
     int32_t full;       // 1: a third score was within delta -> full fp32 rescan
 };
 
+// rows whose third-best score is also within delta: rescanned against every reference in fp32 (K3b).
+// K2 appends the row, zeroes its packed-result key and the arrival counter of its group of kFullGroup rows.
+constexpr int kFullGroup = 8;
+struct WsHeader;
+struct RecheckLists {
+    WsHeader* hdr;
+    RecheckRec* recs;          // near-tie / near-threshold rows: two-candidate fp32 check (K3a)
+    int64_t rec_cap;
+    int32_t* full_rows;        // rows needing the full rescan (K3b)
+    unsigned long long* full_keys;   // per full row: (orderable(best) << 32) | ~idx, combined with atomicMax
+    int32_t* full_ctr;         // per group of kFullGroup full rows: blocks that have contributed
+    int64_t full_cap;
+};
+
 // workspace header shared by all filter paths (device memory, 256 B)
 struct WsHeader {
     int32_t recheck_count;   // rows appended to the recheck list
@@ -204,10 +218,10 @@ int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64
                        float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
 int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                      WsHeader* hdr, RecheckRec* recs, int64_t rec_cap, int no_recheck, cudaStream_t s);
+                      RecheckLists lists, int no_recheck, cudaStream_t s);
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
                    const float* ref_norm, const float* cand_norm, float thr, int64_t ref_index_base,
-                   uint8_t* keep, int32_t* idx, float* val, const WsHeader* hdr, const RecheckRec* recs, int64_t rec_cap,
+                   uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                    float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
 int launch_ref_stats(const float* ref_feat, int32_t n_ref, int32_t dim, float* mean, float* thres, cudaStream_t s);
 int launch_pack_results(const uint8_t* keep, const int32_t* idx, int64_t m, int64_t m_pad, uint8_t* packed,
@@ -215,7 +229,7 @@ int launch_pack_results(const uint8_t* keep, const int32_t* idx, int64_t m, int6
 int launch_unpack_results(const uint8_t* packed, int64_t m, int64_t m_pad, int nranks, uint8_t* keep, int32_t* idx,
                           cudaStream_t s);
 int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
-                            float thr, float delta, uint8_t* keep, int32_t* idx, float* val, WsHeader* hdr,
-                            RecheckRec* recs, int64_t rec_cap, float* scores, cudaStream_t s);
+                            float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
+                            float* scores, cudaStream_t s);
 
 }  // namespace ffr

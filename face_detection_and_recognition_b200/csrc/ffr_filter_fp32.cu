@@ -89,9 +89,19 @@ filter_fp32_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
             if (i < n_ref) load_row<NV>(ref + static_cast<int64_t>(i) * dim, dim, lane, rreg[i], false);
     }
 
-    for (int64_t row = warp; row < n_cand; row += nwarps) {
-        float4 c[NV];
-        load_row<NV>(cand + row * dim, dim, lane, c, true);
+    // kRowsInFlight candidate rows are loaded before any is consumed, so that every warp keeps several
+    // independent 512-byte requests outstanding (HBM latency x bandwidth needs ~40 KB in flight per SM)
+    constexpr int kRowsInFlight = (NV <= 2) ? 4 : 2;
+    for (int64_t row0 = warp * kRowsInFlight; row0 < n_cand; row0 += nwarps * kRowsInFlight) {
+      float4 cbuf[kRowsInFlight][NV];
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u)
+        if (row0 + u < n_cand) load_row<NV>(cand + (row0 + u) * dim, dim, lane, cbuf[u], true);
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const int64_t row = row0 + u;
+        if (row >= n_cand) break;
+        float4 (&c)[NV] = cbuf[u];
         float cc_sqrt = 0.f;
         if (kCosine) {
             float cc = 0.f;
@@ -134,6 +144,7 @@ filter_fp32_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
                 if (band.rows != nullptr && slot < band.cap) band.rows[slot] = row;
             }
         }
+      }
     }
 }
 

@@ -90,8 +90,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                   int64_t n_ref, int64_t n_cand, int32_t kb_count, int32_t a_stages, int32_t b_stages,
                   float thr, float delta, float thr_band, int64_t ref_index_base,
                   uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx, float* __restrict__ best_val,
-                  WsHeader* __restrict__ hdr, RecheckRec* __restrict__ recs, int64_t rec_cap, int no_recheck,
-                  float* __restrict__ dbg_scores) {
+                  RecheckLists lists, int no_recheck, float* __restrict__ dbg_scores) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is not guaranteed to have it.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,24 +248,35 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 best_idx[row] = static_cast<int32_t>(t.i1 + ref_index_base);
                 if (best_val != nullptr) best_val[row] = t.b1;
             }
-            const uint32_t fmask = __ballot_sync(0xffffffffu, flagged);
-            if (fmask != 0) {
-                const uint32_t umask = __ballot_sync(0xffffffffu, full);
+            const bool pair = flagged && !full;
+            const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
+            const uint32_t umask = __ballot_sync(0xffffffffu, full);
+            if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
                 int32_t slot0 = 0;
-                if (lane == 0) {
-                    slot0 = atomicAdd(&hdr->recheck_count, __popc(fmask));
-                    if (umask != 0) atomicAdd(&hdr->full_count, __popc(umask));
-                }
+                if (lane == 0) slot0 = atomicAdd(&lists.hdr->recheck_count, __popc(pmask));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (flagged) {
-                    const int64_t slot = slot0 + __popc(fmask & ((1u << lane) - 1));
-                    if (slot < rec_cap) {
+                if (pair) {
+                    const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
+                    if (slot < lists.rec_cap) {
                         RecheckRec r;
                         r.row = static_cast<int32_t>(row);
                         r.idx1 = t.i1;
                         r.idx2 = near_tie ? t.i2 : -1;
-                        r.full = full ? 1 : 0;
-                        recs[slot] = r;
+                        r.full = 0;
+                        lists.recs[slot] = r;
+                    }
+                }
+            }
+            if (umask != 0) {                                  // ... and to the full-rescan list
+                int32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&lists.hdr->full_count, __popc(umask));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (full) {
+                    const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
+                    if (slot < lists.full_cap) {
+                        lists.full_rows[slot] = static_cast<int32_t>(row);
+                        lists.full_keys[slot] = 0ull;
+                        if (slot % kFullGroup == 0) lists.full_ctr[slot / kFullGroup] = 0;
                     }
                 }
             }
@@ -317,8 +327,7 @@ int make_tmap(CUtensorMap* m, const __half* base, int64_t rows, int32_t ld, int3
 
 int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                           WsHeader* hdr, RecheckRec* recs, int64_t rec_cap, int no_recheck, float* dbg_scores,
-                           cudaStream_t s) {
+                           RecheckLists lists, int no_recheck, float* dbg_scores, cudaStream_t s) {
     if (dim_pad % kBlockK != 0 || dim_pad < kBlockK || dim_pad > 512) {
         set_error("filter_mma: padded dim %d not in {64..512 step 64}", dim_pad);
         return FFR_ERR_UNSUPPORTED;
@@ -351,8 +360,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     const int sms = num_sms();
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
     filter_mma_kernel<<<grid, kThreads, smem, s>>>(tm_c, tm_r, n_ref, n_cand, kb, a_stages, b_stages, thr, delta, thr_band,
-                                                   ref_index_base, keep, idx, val, hdr, recs, rec_cap, no_recheck,
-                                                   dbg_scores);
+                                                   ref_index_base, keep, idx, val, lists, no_recheck, dbg_scores);
     FFR_LAUNCH_CHECK("filter_mma");
     return FFR_OK;
 }
@@ -361,17 +369,17 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
 
 int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                      WsHeader* hdr, RecheckRec* recs, int64_t rec_cap, int no_recheck, cudaStream_t s) {
+                      RecheckLists lists, int no_recheck, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, cand16, n_cand, dim_pad, thr, delta, thr_band, ref_index_base, keep, idx, val,
-                                  hdr, recs, rec_cap, no_recheck, nullptr, s);
+                                  lists, no_recheck, nullptr, s);
 }
 
 // test hook (not part of the ABI in include/ffr.h): additionally dumps the full score matrix
 int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
-                            float thr, float delta, uint8_t* keep, int32_t* idx, float* val, WsHeader* hdr,
-                            RecheckRec* recs, int64_t rec_cap, float* scores, cudaStream_t s) {
-    return launch_filter_mma_impl(ref16, n_ref, cand16, n_cand, dim_pad, thr, delta, delta, 0, keep, idx, val, hdr, recs,
-                                  rec_cap, 0, scores, s);
+                            float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
+                            float* scores, cudaStream_t s) {
+    return launch_filter_mma_impl(ref16, n_ref, cand16, n_cand, dim_pad, thr, delta, delta, 0, keep, idx, val, lists, 0,
+                                  scores, s);
 }
 
 }  // namespace ffr

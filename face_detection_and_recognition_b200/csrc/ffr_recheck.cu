@@ -41,50 +41,177 @@ __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, cons
     return __fdiv_rn(a, __fmul_rn(__fsqrt_rn(b), cc_sqrt));
 }
 
+__device__ __forceinline__ void emit_result(int32_t row, float best, int32_t bi, float thr, int64_t ref_index_base,
+                                            uint8_t* keep, int32_t* best_idx, float* best_val, float band_tol,
+                                            int32_t* band_count, int64_t* band_rows, int64_t band_cap) {
+    keep[row] = (best >= thr) ? 1 : 0;
+    best_idx[row] = static_cast<int32_t>(bi + ref_index_base);
+    if (best_val != nullptr) best_val[row] = best;
+    if (band_count != nullptr && fabsf(best - thr) <= band_tol) {
+        const int32_t slot = atomicAdd(band_count, 1);
+        if (band_rows != nullptr && slot < band_cap) band_rows[slot] = row;
+    }
+}
+
+// K3a: near-tie / near-threshold rows -- fp32 cosine against the one or two leading references. One warp per row.
 __global__ void __launch_bounds__(kThreads)
-recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
-               int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
-               float* __restrict__ best_val, const WsHeader* __restrict__ hdr, const RecheckRec* __restrict__ recs,
-               int64_t rec_cap, float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, int vec) {
+recheck_pairs_kernel(const float* __restrict__ ref, const float* __restrict__ cand, int32_t dim, float thr,
+                     int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+                     float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
+                     int64_t* band_rows, int64_t band_cap, int vec) {
     extern __shared__ __align__(16) float s_rows[];            // kWarps x dim
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* c_smem = s_rows + static_cast<size_t>(w) * dim;
-    int64_t count = hdr->recheck_count;
-    if (count > rec_cap) count = rec_cap;
+    int64_t count = lists.hdr->recheck_count;
+    if (count > lists.rec_cap) count = lists.rec_cap;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
     for (int64_t k = warp; k < count; k += nwarps) {
-        const RecheckRec rec = recs[k];
+        const RecheckRec rec = lists.recs[k];
         const float* c = cand + static_cast<int64_t>(rec.row) * dim;
         float cc = 0.f;
         __syncwarp();
         for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
         __syncwarp();
         const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
-        float best;
-        int32_t bi;
-        if (rec.full) {
-            best = -INFINITY;
-            bi = 0;
-            for (int64_t i = 0; i < n_ref; ++i) {
-                const float s = cos_fp32(c_smem, ref + i * dim, dim, cc_sqrt, lane, vec != 0);
-                if (s > best || i == 0) { best = s; bi = static_cast<int32_t>(i); }
+        float best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec != 0);
+        int32_t bi = rec.idx1;
+        if (rec.idx2 >= 0) {
+            const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec != 0);
+            if (s2 > best || (s2 == best && rec.idx2 < bi)) { best = s2; bi = rec.idx2; }
+        }
+        if (lane == 0)
+            emit_result(rec.row, best, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
+                        band_rows, band_cap);
+    }
+}
+
+// K3b: rows with three or more references inside the window -- exact fp32 rescan of the WHOLE reference set.
+// A block owns kFullGroup candidate rows (parked in shared memory) and one slice of the references; every thread
+// walks its own reference rows (thread-per-reference: no shuffles, each reference row is read once per group and
+// reused for all kFullGroup candidates), keeps a per-candidate best with strict '>' in ascending order, and the
+// block/ slice results are merged with a 64-bit atomicMax on (orderable(score) << 32 | ~index), which implements
+// "largest score, then smallest index" = np.argmax.  The last slice to arrive writes the outputs.
+__device__ __forceinline__ unsigned long long pack_key(float v, int32_t idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(idx));
+}
+__device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32_t& idx) {
+    uint32_t u = static_cast<uint32_t>(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    v = __uint_as_float(u);
+    idx = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFull));
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads)
+rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
+                   int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+                   float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
+                   int64_t* band_rows, int64_t band_cap) {
+    extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows
+    __shared__ float s_ccs[kFullGroup];
+    __shared__ unsigned long long s_key[kWarps][kFullGroup];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t count = lists.hdr->full_count;
+    if (count > lists.full_cap) count = lists.full_cap;
+    const int splits = gridDim.y;
+    const int64_t per = (n_ref + splits - 1) / splits;
+    const int64_t lo = static_cast<int64_t>(blockIdx.y) * per;
+    const int64_t hi = (lo + per < n_ref) ? lo + per : n_ref;
+    const int64_t n_groups = (count + kFullGroup - 1) / kFullGroup;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        __syncthreads();
+        // warp w parks candidate row w of the group (kWarps == kFullGroup)
+        {
+            const int64_t slot = g * kFullGroup + w;
+            float cc = 0.f;
+            if (slot < count) {
+                const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
+                for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); s_c[w * dim + d] = t; cc = fmaf(t, t, cc); }
+            } else {
+                for (int d = lane; d < dim; d += 32) s_c[w * dim + d] = 0.f;
             }
-        } else {
-            best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec != 0);
-            bi = rec.idx1;
-            if (rec.idx2 >= 0) {
-                const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec != 0);
-                if (s2 > best || (s2 == best && rec.idx2 < bi)) { best = s2; bi = rec.idx2; }
+            cc = warp_sum(cc);
+            if (lane == 0) s_ccs[w] = __fsqrt_rn(cc);
+        }
+        __syncthreads();
+        float best[kFullGroup];
+        int32_t bidx[kFullGroup];
+#pragma unroll
+        for (int j = 0; j < kFullGroup; ++j) { best[j] = -INFINITY; bidx[j] = 0x7FFFFFFF; }
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+            float acc[kFullGroup];
+#pragma unroll
+            for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
+            float rr = 0.f;
+            const float* r = ref + i * dim;
+            if (kVec) {
+                const float4* r4 = reinterpret_cast<const float4*>(r);
+                const float4* c4 = reinterpret_cast<const float4*>(s_c);
+                const int nv = dim >> 2;
+#pragma unroll 2
+                for (int k = 0; k < nv; ++k) {
+                    const float4 rv = __ldg(r4 + k);
+                    rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
+#pragma unroll
+                    for (int j = 0; j < kFullGroup; ++j) {
+                        const float4 cv = c4[j * nv + k];          // same address across the warp: broadcast
+                        acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
+                        acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
+                    }
+                }
+            } else {
+                for (int k = 0; k < dim; ++k) {
+                    const float rv = __ldg(r + k);
+                    rr = fmaf(rv, rv, rr);
+#pragma unroll
+                    for (int j = 0; j < kFullGroup; ++j) acc[j] = fmaf(s_c[j * dim + k], rv, acc[j]);
+                }
+            }
+            const float rs = __fsqrt_rn(rr);
+#pragma unroll
+            for (int j = 0; j < kFullGroup; ++j) {
+                const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
+                if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
             }
         }
-        if (lane == 0) {
-            keep[rec.row] = (best >= thr) ? 1 : 0;
-            best_idx[rec.row] = static_cast<int32_t>(bi + ref_index_base);
-            if (best_val != nullptr) best_val[rec.row] = best;
-            if (band_count != nullptr && fabsf(best - thr) <= band_tol) {
-                const int32_t slot = atomicAdd(band_count, 1);
-                if (band_rows != nullptr && slot < band_cap) band_rows[slot] = rec.row;
+        // block merge: warp shuffle max on the packed key, then one atomicMax per (warp, row)
+#pragma unroll
+        for (int j = 0; j < kFullGroup; ++j) {
+            unsigned long long key = (bidx[j] == 0x7FFFFFFF) ? 0ull : pack_key(best[j], bidx[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0) s_key[w][j] = key;
+        }
+        __syncthreads();
+        if (threadIdx.x < kFullGroup) {
+            const int j = threadIdx.x;
+            unsigned long long key = 0ull;
+            for (int ww = 0; ww < kWarps; ++ww) key = s_key[ww][j] > key ? s_key[ww][j] : key;
+            const int64_t slot = g * kFullGroup + j;
+            if (slot < count && key != 0ull) atomicMax(&lists.full_keys[slot], key);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&lists.full_ctr[g], 1) == splits - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last && threadIdx.x < kFullGroup) {
+            __threadfence();
+            const int64_t slot = g * kFullGroup + threadIdx.x;
+            if (slot < count) {
+                const unsigned long long key = atomicAdd(&lists.full_keys[slot], 0ull);     // coherent read
+                float v;
+                int32_t bi;
+                unpack_key(key, v, bi);
+                if (key == 0ull) { v = -INFINITY; bi = 0; }
+                emit_result(lists.full_rows[slot], v, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol,
+                            band_count, band_rows, band_cap);
             }
         }
     }
@@ -118,20 +245,35 @@ __global__ void unpack_results_kernel(const uint8_t* __restrict__ packed, int64_
 
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
                    const float* /*ref_norm*/, const float* /*cand_norm*/, float thr, int64_t ref_index_base,
-                   uint8_t* keep, int32_t* idx, float* val, const WsHeader* hdr, const RecheckRec* recs, int64_t rec_cap,
+                   uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                    float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s) {
     if (n_cand == 0) return FFR_OK;
+    static_assert(kWarps == kFullGroup, "one warp parks one candidate row of a full-rescan group");
     const int sms = num_sms();
     const size_t smem = static_cast<size_t>(kWarps) * dim * sizeof(float);
     if (smem > 48 * 1024) { set_error("recheck: dim %d too large", dim); return FFR_ERR_UNSUPPORTED; }
     const int vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(ref) & 15) == 0);
-    // the flagged-row count lives on the device; a fixed grid strides over it
+    // the flagged-row counts live on the device; fixed grids stride over them (idle blocks exit at once)
     int64_t grid = (n_cand + kWarps - 1) / kWarps;
     if (grid > static_cast<int64_t>(sms) * 4) grid = static_cast<int64_t>(sms) * 4;
-    recheck_kernel<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep,
-                                                                       idx, val, hdr, recs, rec_cap, band_tol,
-                                                                       band_count, band_rows, band_cap, vec);
-    FFR_LAUNCH_CHECK("recheck");
+    recheck_pairs_kernel<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(ref, cand, dim, thr, ref_index_base, keep,
+                                                                             idx, val, lists, band_tol, band_count,
+                                                                             band_rows, band_cap, vec);
+    FFR_LAUNCH_CHECK("recheck_pairs");
+    // full rescans: slice the reference axis so that even a handful of rows spreads over the chip
+    int splits = static_cast<int>(n_ref / 2048);
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
+    int64_t groups = (n_cand + kFullGroup - 1) / kFullGroup;
+    int64_t gx = (static_cast<int64_t>(sms) * 4 + splits - 1) / splits;
+    if (gx > groups) gx = groups;
+    if (gx < 1) gx = 1;
+    const dim3 g2(static_cast<unsigned>(gx), static_cast<unsigned>(splits));
+    if (vec) rescan_full_kernel<true><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                                                  lists, band_tol, band_count, band_rows, band_cap);
+    else     rescan_full_kernel<false><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                                                   lists, band_tol, band_count, band_rows, band_cap);
+    FFR_LAUNCH_CHECK("rescan_full");
     return FFR_OK;
 }
 

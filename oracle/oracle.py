@@ -150,6 +150,27 @@ def filter_cosine(ref: np.ndarray, cand: np.ndarray, thr: float, block: int = 81
     return keep, idx, best.astype(dtype)
 
 
+def filter_cosine_torch(ref: np.ndarray, cand: np.ndarray, thr: float, block: int = 16384):
+    """Same restatement as ``filter_cosine`` with torch-CPU doing the sgemm / max / argmax (multi-threaded MKL): the
+    fastest CPU form of the reference's arithmetic, used as the CPU baseline in bench.py.  torch.max over dim 0 returns
+    the first maximal index like np.argmax."""
+    import torch
+    with torch.no_grad():
+        r = torch.from_numpy(np.ascontiguousarray(ref, dtype=np.float32))
+        rn = r / torch.linalg.vector_norm(r, dim=1, keepdim=True)
+        m = cand.shape[0]
+        best = torch.empty(m, dtype=torch.float32)
+        idx = torch.empty(m, dtype=torch.int64)
+        for s in range(0, m, block):
+            c = torch.from_numpy(np.ascontiguousarray(cand[s:s + block], dtype=np.float32))
+            cn = c / torch.linalg.vector_norm(c, dim=1, keepdim=True)
+            sim = rn @ cn.T
+            b, i = torch.max(sim, dim=0)
+            best[s:s + block], idx[s:s + block] = b, i
+        keep = (best >= thr).to(torch.uint8)
+    return keep.numpy(), idx.numpy().astype(np.int32), best.numpy()
+
+
 def filter_euclid(ref: np.ndarray, cand: np.ndarray, thr: float, block: int = 4096,
                   dtype=np.float32) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Gallery Euclid filter: ``best = min_i |c - r_i|`` (filter_faces...:189 when ref = {mean}),

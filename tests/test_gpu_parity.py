@@ -166,7 +166,7 @@ def test_mma_raw_scores(ffr_lib, ops, n_ref, n_cand, dim):
     keep = torch.empty(n_cand, dtype=torch.uint8, device="cuda")
     idx = torch.empty(n_cand, dtype=torch.int32, device="cuda")
     val = torch.empty(n_cand, dtype=torch.float32, device="cuda")
-    ws = torch.zeros(256 + 16 * n_cand + 256, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(4096 + 64 * n_cand, dtype=torch.uint8, device="cuda")
     from face_detection_and_recognition_b200._lib import check
     check(ffr_lib.ffr_debug_mma_scores(r16.data_ptr(), n_ref, c16.data_ptr(), n_cand, ld, 0.5, keep.data_ptr(),
                                        idx.data_ptr(), val.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(),

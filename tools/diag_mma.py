@@ -24,7 +24,7 @@ def raw(n_ref, n_cand, dim):
     keep = torch.empty(n_cand, dtype=torch.uint8, device="cuda")
     idx = torch.empty(n_cand, dtype=torch.int32, device="cuda")
     val = torch.empty(n_cand, dtype=torch.float32, device="cuda")
-    ws = torch.zeros(512 + 16 * n_cand, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(4096 + 64 * n_cand, dtype=torch.uint8, device="cuda")
     rc = lib.ffr_debug_mma_scores(r16.data_ptr(), n_ref, c16.data_ptr(), n_cand, ld, 0.5, keep.data_ptr(),
                                   idx.data_ptr(), val.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(),
                                   torch.cuda.current_stream().cuda_stream)
