@@ -58,6 +58,7 @@ HOOKS = {
     "ffr_set_recheck_delta": (None, [_f32]),
     "ffr_get_recheck_delta": (_f32, []),
     "ffr_debug_set_k2_events": (None, [_vp, _vp]),
+    "ffr_debug_set_prof": (None, [_vp]),
     "ffr_debug_mma_scores": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -205,6 +205,8 @@ int64_t ffr_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 // not in the public header: tuning / test hooks
 void ffr_set_recheck_delta(float d) { g_delta = d; }
+// device buffer [grid][16] u64 that the tcgen05 kernel fills with stall-cycle counters (NULL to disable)
+void ffr_debug_set_prof(void* dev_ptr) { set_mma_prof_buffer(static_cast<unsigned long long*>(dev_ptr)); }
 // cudaEvent_t pair recorded around the next tcgen05 kernel launches of this thread (NULL, NULL to disable)
 void ffr_debug_set_k2_events(void* begin, void* end) {
     g_ev_k2_begin = static_cast<cudaEvent_t>(begin);

@@ -13,13 +13,18 @@
 // |score - fp32 score| ~ 2e-5 rms (<= ~1.5e-4 observed), which is why K3 re-checks in fp32 every row whose
 // top-2 gap or distance to the threshold is <= delta.
 //
-// Decomposition (one CTA per SM, persistent over candidate tiles):
+// Decomposition (one CTA per SM, persistent over candidate tiles; template kCG = tcgen05 cta_group):
 //   * candidates -> MMA M (TMEM lanes), references -> MMA N (TMEM columns).  A CTA keeps its 128-candidate
 //     A tile (all of K) resident in shared memory and streams 256-reference B tiles, K-block by K-block,
 //     out of L2 through a TMA/mbarrier ring: per 128 x 256 x K tile only B moves.
-//   * warp 0: TMA producer.  warp 1: tcgen05.mma issuer (single thread) + TMEM owner.  warps 2-5: epilogue,
-//     one thread per candidate row (TMEM lane), so the max/argmax over references is a pure in-register
-//     reduction over columns -- no shuffles, no shared memory.
+//   * kCG == 2: two CTAs of a cluster (an SM pair) share every B tile -- each loads half of it and one
+//     tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA reads A and B from both CTAs' shared memory
+//     and writes 128 accumulator rows into each CTA's TMEM.  Half the B bytes per SM from L2, and a ring that
+//     is twice as deep in time for the same shared memory.
+//   * warp 0: TMA producer.  warp 1: tcgen05.mma issuer (single thread, leader CTA) + TMEM owner.
+//     warps 2-9: epilogue, one thread per (candidate row, column half): the max/argmax over references is a
+//     pure in-register reduction over TMEM columns -- no shuffles; the two column halves of a row are merged
+//     through 2.5 KB of shared memory once per candidate tile.
 //   * the accumulator is double buffered in TMEM (2 x 256 of the 512 columns): the MMAs of reference tile
 //     t+1 overlap the epilogue of tile t.
 //   * epilogue per 32-column chunk: tcgen05.ld -> max tree (3-input max) -> only if the chunk max comes
@@ -27,6 +32,7 @@
 //     top-3 {best, idx} {second, idx} third.  Ascending column order + strict '>' = np.argmax first
 //     occurrence.  The top-3 is what K3 needs to make the index and keep bit exact in fp32.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ffr_common.cuh"
 
@@ -34,18 +40,18 @@ namespace ffr {
 
 namespace {
 
-constexpr int kTileM = 128;          // candidates per CTA tile
-constexpr int kTileN = 256;          // references per accumulator stage
+constexpr int kTileM = 128;          // candidates per CTA tile (TMEM lanes)
+constexpr int kTileN = 256;          // references per accumulator stage (TMEM columns)
 constexpr int kBlockK = 64;          // fp16 per 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;        // warp 0 TMA | warp 1 MMA | warps 2..5 epilogue
 constexpr int kMaxAStages = 4;
-constexpr int kMaxBStages = 8;
+constexpr int kMaxBStages = 12;
 constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-block of the A tile
-constexpr uint32_t kBStageBytes = kTileN * kBlockK * 2;      // 32 KiB: one K-block of a B tile
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;                       // 227 KiB opt-in maximum
-constexpr uint32_t kBarrierBytes = 1024;
+constexpr uint32_t kBarrierBytes = 512;                       // mbarriers + TMEM slot
+constexpr uint32_t kMergeBytes = kTileM * 5 * 4;              // top-3 hand-over of the upper column half
+// per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
 struct Top3 {
     float b1, b2, b3;
@@ -54,6 +60,18 @@ struct Top3 {
 
 __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
     const bool g1 = v > t.b1, g2 = v > t.b2, g3 = v > t.b3;
+    t.b3 = g2 ? t.b2 : (g3 ? v : t.b3);
+    t.i2 = g1 ? t.i1 : (g2 ? idx : t.i2);
+    t.b2 = g1 ? t.b1 : (g2 ? v : t.b2);
+    t.i1 = g1 ? idx : t.i1;
+    t.b1 = g1 ? v : t.b1;
+}
+
+// merge variant: the two column halves interleave in index order, so ties are broken by the smaller index
+__device__ __forceinline__ void top3_merge_insert(Top3& t, float v, int32_t idx) {
+    const bool g1 = (v > t.b1) || (v == t.b1 && idx < t.i1);
+    const bool g2 = (v > t.b2) || (v == t.b2 && idx < t.i2);
+    const bool g3 = v > t.b3;
     t.b3 = g2 ? t.b2 : (g3 ? v : t.b3);
     t.i2 = g1 ? t.i1 : (g2 ? idx : t.i2);
     t.b2 = g1 ? t.b1 : (g2 ? v : t.b2);
@@ -85,209 +103,397 @@ __device__ __forceinline__ void mask_chunk(float (&v)[32], int valid) {
     for (int j = 0; j < 32; ++j) v[j] = (j < valid) ? v[j] : -INFINITY;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// ---- cluster / cta_group::2 PTX -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's CTA 0
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // arrive on CTA 0's copy of the barrier
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1,
+                                                uint64_t cache_hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(cache_hint)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {         // arrives on the barrier in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool on, unsigned long long& acc) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += static_cast<unsigned long long>(clock64() - t0);
+}
+
+struct KParams {
+    int64_t n_ref, n_cand;
+    int32_t kb_count, a_stages, b_stages;
+    float thr, delta, thr_band;
+    int64_t ref_index_base;
+    uint8_t* keep;
+    int32_t* best_idx;
+    float* best_val;
+    RecheckLists lists;
+    int no_recheck;
+    float* dbg_scores;
+    int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
+    unsigned long long* prof;      // optional [gridDim.x][16] stall-cycle counters (diagnostics)
+};
+
+// kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8|16) = 4 TMEM lane quadrants x kEW/4 column parts.
+template <int kCG, int kEW>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
-                  int64_t n_ref, int64_t n_cand, int32_t kb_count, int32_t a_stages, int32_t b_stages,
-                  float thr, float delta, float thr_band, int64_t ref_index_base,
-                  uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx, float* __restrict__ best_val,
-                  RecheckLists lists, int no_recheck, float* __restrict__ dbg_scores) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is not guaranteed to have it.
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_stage_bytes = static_cast<uint32_t>(kb_count) * kABlockBytes;
+                  const KParams p) {
+    constexpr int kParts = kEW / 4;                                 // column parts per reference tile
+    constexpr int kChunksPerPart = (kTileN / 32) / kParts;
+    constexpr uint32_t kBRows = kTileN / kCG;                       // B rows this CTA loads per K-block
+    constexpr uint32_t kBStageBytes = kBRows * kBlockK * 2;         // 32 KiB (kCG 1) / 16 KiB (kCG 2)
+    extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t a_stage_bytes = static_cast<uint32_t>(p.kb_count) * kABlockBytes;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem_a + static_cast<size_t>(a_stages) * a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(b_stages) * kBStageBytes);
-    uint64_t* a_full = bars;
+    uint8_t* smem_b = smem_a + static_cast<size_t>(p.a_stages) * a_stage_bytes;
+    uint8_t* extra = smem_b + static_cast<size_t>(p.b_stages) * kBStageBytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(extra);
     uint64_t* a_empty = a_full + kMaxAStages;
     uint64_t* b_full = a_empty + kMaxAStages;
     uint64_t* b_empty = b_full + kMaxBStages;
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][5][kTileM]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int64_t n_tiles = (n_cand + kTileM - 1) / kTileM;
-    const int32_t n_rt = static_cast<int32_t>((n_ref + kTileN - 1) / kTileN);
+    const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int64_t n_tiles = (p.n_cand + kTileM * kCG - 1) / (kTileM * kCG);   // tiles of the CTA pair
+    const int64_t tile0 = blockIdx.x / kCG, tile_stride = gridDim.x / kCG;
+    const int32_t n_rt = static_cast<int32_t>((p.n_ref + kTileN - 1) / kTileN);
 
     if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
         tma_prefetch_desc(&tmap_cand);
         tma_prefetch_desc(&tmap_ref);
         for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if (kCG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
+        else          tmem_alloc<kTmemCols>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Keeping the warp
+        // converged matters: UTMALDG / UTCHMMA are uniform-datapath instructions and inside a divergent region
+        // ptxas wraps each of them in a serialising vote loop (~200 cycles per MMA issue, measured).
+        {
             uint32_t a_it = 0, b_it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint32_t as = a_it % a_stages, aph = (a_it / a_stages) & 1;
-                mbar_wait(&a_empty[as], aph ^ 1);
-                mbar_expect_tx(&a_full[as], a_stage_bytes);
-                for (int kb = 0; kb < kb_count; ++kb)
-                    tma_load_2d(smem_a + as * a_stage_bytes + kb * kABlockBytes, &tmap_cand, &a_full[as],
-                                kb * kBlockK, static_cast<int32_t>(tile * kTileM), kEvictFirst);
+            const bool pr = p.prof != nullptr;
+            unsigned long long w_aempty = 0, w_bempty = 0;
+            const long long t_begin = clock64();
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+                const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
+                const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
+                mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_aempty);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
+                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                        else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                    }
+                }
+                __syncwarp();
                 ++a_it;
                 for (int rt = 0; rt < n_rt; ++rt) {
-                    for (int kb = 0; kb < kb_count; ++kb) {
-                        const uint32_t bs = b_it % b_stages, bph = (b_it / b_stages) & 1;
-                        mbar_wait(&b_empty[bs], bph ^ 1);
-                        mbar_expect_tx(&b_full[bs], kBStageBytes);
-                        tma_load_2d(smem_b + bs * kBStageBytes, &tmap_ref, &b_full[bs], kb * kBlockK, rt * kTileN,
-                                    kEvictLast);
+                    const int32_t rrow0 = rt * kTileN + static_cast<int32_t>(cta_rank * kBRows);
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1;
+                        mbar_wait_timed(&b_empty[bs], bph ^ 1, pr, w_bempty);
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(&b_full[bs], kBStageBytes * kCG);
+                            uint8_t* dst = smem_b + bs * kBStageBytes;
+                            if (kCG == 2) tma_load_2d_cg2(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
+                            else          tma_load_2d(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
+                        }
+                        __syncwarp();
                         ++b_it;
                     }
                 }
+            }
+            if (pr && lane == 0) {
+                p.prof[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
+                p.prof[blockIdx.x * 16 + 1] = w_aempty;
+                p.prof[blockIdx.x * 16 + 2] = w_bempty;
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader CTA; whole warp converged, one elected lane issues) ==========
+        if (leader) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint32_t as = a_it % a_stages, aph = (a_it / a_stages) & 1;
-                mbar_wait(&a_full[as], aph);
+            const bool pr = p.prof != nullptr;
+            unsigned long long w_afull = 0, w_tempty = 0, w_bfull = 0;
+            const long long t_begin = clock64();
+            // UMMA smem descriptor, K-major SWIZZLE_128B: hi word is constant (SBO 1024 B, version 1, layout 2);
+            // lo word = (address >> 4) | LBO(1) << 16, advanced by 2 (32 bytes) per K = 16 step.
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+                const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
+                mbar_wait_timed(&a_full[as], aph, pr, w_afull);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(smem_a + as * a_stage_bytes);
+                const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const uint32_t acc = t_it & 1, tph = (t_it >> 1) & 1;
-                    mbar_wait(&t_empty[acc], tph ^ 1);
+                    mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
-                    int64_t ncols = n_ref - static_cast<int64_t>(rt) * kTileN;
-                    if (ncols > kTileN) ncols = kTileN;
-                    const uint32_t n_mma = static_cast<uint32_t>((ncols + 15) & ~int64_t(15));
-                    const uint32_t idesc = umma_idesc_f16(kTileM, n_mma);
+                    uint32_t n_mma = kTileN;
+                    if (kCG == 1) {                             // tail reference tile: only as many columns as needed
+                        int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kTileN;
+                        if (ncols < kTileN) n_mma = static_cast<uint32_t>((ncols + 15) & ~int64_t(15));
+                    }
+                    const uint32_t idesc = umma_idesc_f16(kTileM * kCG, n_mma);
                     const uint32_t d_tmem = tmem_base + acc * kTileN;
-                    for (int kb = 0; kb < kb_count; ++kb) {
-                        const uint32_t bs = b_it % b_stages, bph = (b_it / b_stages) & 1;
-                        mbar_wait(&b_full[bs], bph);
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1;
+                        mbar_wait_timed(&b_full[bs], bph, pr, w_bfull);
                         tc_fence_after();
-                        const uint32_t b_base = smem_u32(smem_b + bs * kBStageBytes);
+                        const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
+                        const uint32_t b_lo = ((smem_u32(smem_b + bs * kBStageBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            const uint64_t da = umma_desc_sw128(a_base + kb * kABlockBytes + k * (kUmmaK * 2));
-                            const uint64_t db = umma_desc_sw128(b_base + k * (kUmmaK * 2));
-                            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2u * k);
+                                const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2u * k);
+                                if (kCG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                else          umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
                         }
-                        umma_commit(&b_empty[bs]);            // B stage reusable once these MMAs retire
+                        __syncwarp();
                         ++b_it;
                     }
-                    umma_commit(&t_full[acc]);                // accumulator complete -> epilogue
+                    if (elect_one()) {
+                        if (kCG == 2) umma_commit_cg2(&t_full[acc]); else umma_commit(&t_full[acc]);   // accumulator ready
+                    }
+                    __syncwarp();
                     ++t_it;
                 }
-                umma_commit(&a_empty[as]);                    // A stage reusable
+                if (elect_one()) {
+                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);       // A stage reusable
+                }
+                __syncwarp();
                 ++a_it;
+            }
+            if (pr && lane == 0) {
+                p.prof[blockIdx.x * 16 + 4] = static_cast<unsigned long long>(clock64() - t_begin);
+                p.prof[blockIdx.x * 16 + 5] = w_afull;
+                p.prof[blockIdx.x * 16 + 6] = w_tempty;
+                p.prof[blockIdx.x * 16 + 7] = w_bfull;
+                p.prof[blockIdx.x * 16 + 8] = t_it;
             }
         }
     } else {
-        // ===================== epilogue: one thread per candidate row =====================
+        // ===================== epilogue: one thread per (candidate row, column half) =====================
         const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int h = (warp - 2) >> 2;                        // column part of every reference tile this warp scans
+        const int r_in_tile = q * 32 + lane;
         uint32_t t_it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        bool first_tile = true;
+        const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
+        unsigned long long w_tfull = 0;
+        const long long t_begin = clock64();
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
             t.b1 = t.b2 = t.b3 = -INFINITY;
             t.i1 = 0;
             t.i2 = -1;
-            const int64_t row = tile * kTileM + q * 32 + lane;
+            const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
                 const uint32_t acc = t_it & 1, tph = (t_it >> 1) & 1;
-                mbar_wait(&t_full[acc], tph);
+                mbar_wait_timed(&t_full[acc], tph, pr, w_tfull);
                 tc_fence_after();
-                int64_t ncols64 = n_ref - static_cast<int64_t>(rt) * kTileN;
+                int64_t ncols64 = p.n_ref - static_cast<int64_t>(rt) * kTileN;
                 const int ncols = ncols64 > kTileN ? kTileN : static_cast<int>(ncols64);
-                const int nchunks = (ncols + 31) >> 5;
+                const int c_beg = kChunksPerPart * h;
+                const int c_end = min((ncols + 31) >> 5, c_beg + kChunksPerPart);   // this warp's chunks: [c_beg, c_end)
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN;
                 const int32_t col0 = rt * kTileN;
+                // stream this warp's column part out of TMEM chunk by chunk: the next chunk's tcgen05.ld is in flight
+                // while the current one is reduced.  (Measured alternatives that were slower: 16 epilogue warps; loading
+                // the whole part before reducing; a reduce-only first pass that re-reads flagged chunks.)
                 float va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-                for (int c = 0; c < nchunks; c += 2) {
+                if (c_beg < c_end) tmem_ld_32x32(taddr + c_beg * 32, va);
+                for (int c = c_beg; c < c_end; c += 2) {
                     tmem_ld_wait();
-                    if (c + 1 < nchunks) tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                    if (c + 1 < c_end) tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                     if (ncols - c * 32 < 32) mask_chunk(va, ncols - c * 32);
-                    if (dbg_scores != nullptr && row < n_cand) {
+                    if (p.dbg_scores != nullptr && row < p.n_cand) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (col0 + c * 32 + j < n_ref) dbg_scores[row * n_ref + col0 + c * 32 + j] = va[j];
+                            if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = va[j];
                     }
-                    process_chunk(va, col0 + c * 32, delta, t);
-                    if (c + 1 < nchunks) {
+                    if (p.epi_mode == 1) t.b1 = fmax3(t.b1, va[0], va[31]); else
+                    process_chunk(va, col0 + c * 32, p.delta, t);
+                    if (c + 1 < c_end) {
                         tmem_ld_wait();
-                        if (c + 2 < nchunks) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                        if (c + 2 < c_end) tmem_ld_32x32(taddr + (c + 2) * 32, va);
                         if (ncols - (c + 1) * 32 < 32) mask_chunk(vb, ncols - (c + 1) * 32);
-                        if (dbg_scores != nullptr && row < n_cand) {
+                        if (p.dbg_scores != nullptr && row < p.n_cand) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + (c + 1) * 32 + j < n_ref)
-                                    dbg_scores[row * n_ref + col0 + (c + 1) * 32 + j] = vb[j];
+                                if (col0 + (c + 1) * 32 + j < p.n_ref)
+                                    p.dbg_scores[row * p.n_ref + col0 + (c + 1) * 32 + j] = vb[j];
                         }
-                        process_chunk(vb, col0 + (c + 1) * 32, delta, t);
+                        if (p.epi_mode == 1) t.b1 = fmax3(t.b1, vb[0], vb[31]); else
+                        process_chunk(vb, col0 + (c + 1) * 32, p.delta, t);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (lane == 0) {
+                    if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
+                    else                     mbar_arrive(&t_empty[acc]);
+                }
                 ++t_it;
             }
-            // ---- results of this candidate row ----
-            const bool valid = row < n_cand;
-            const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= delta);
-            const bool near_thr = fabsf(t.b1 - thr) <= thr_band;
-            const bool flagged = valid && !no_recheck && (near_tie || near_thr);
-            const bool full = flagged && (t.b1 - t.b3 <= delta);
-            if (valid) {
-                keep[row] = (t.b1 >= thr) ? 1 : 0;
-                best_idx[row] = static_cast<int32_t>(t.i1 + ref_index_base);
-                if (best_val != nullptr) best_val[row] = t.b1;
-            }
-            const bool pair = flagged && !full;
-            const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
-            const uint32_t umask = __ballot_sync(0xffffffffu, full);
-            if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
-                int32_t slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&lists.hdr->recheck_count, __popc(pmask));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (pair) {
-                    const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
-                    if (slot < lists.rec_cap) {
-                        RecheckRec r;
-                        r.row = static_cast<int32_t>(row);
-                        r.idx1 = t.i1;
-                        r.idx2 = near_tie ? t.i2 : -1;
-                        r.full = 0;
-                        lists.recs[slot] = r;
+            // ---- hand the upper column parts over, merge, emit (named barriers 1/2 among the epilogue threads)
+            if (h != 0) {
+                float* mg = merge + (h - 1) * 5 * kTileM;
+                if (!first_tile) named_bar_sync(2, kEW * 32);                  // merge buffer free again
+                mg[0 * kTileM + r_in_tile] = t.b1;
+                mg[1 * kTileM + r_in_tile] = t.b2;
+                mg[2 * kTileM + r_in_tile] = t.b3;
+                mg[3 * kTileM + r_in_tile] = __int_as_float(t.i1);
+                mg[4 * kTileM + r_in_tile] = __int_as_float(t.i2);
+                __threadfence_block();
+                named_bar_arrive(1, kEW * 32);
+            } else {
+                named_bar_sync(1, kEW * 32);
+                float ob1[kParts - 1], ob2[kParts - 1], ob3[kParts - 1];
+                int32_t oi1[kParts - 1], oi2[kParts - 1];
+#pragma unroll
+                for (int pp = 0; pp < kParts - 1; ++pp) {
+                    const float* mg = merge + pp * 5 * kTileM;
+                    ob1[pp] = mg[0 * kTileM + r_in_tile]; ob2[pp] = mg[1 * kTileM + r_in_tile];
+                    ob3[pp] = mg[2 * kTileM + r_in_tile];
+                    oi1[pp] = __float_as_int(mg[3 * kTileM + r_in_tile]);
+                    oi2[pp] = __float_as_int(mg[4 * kTileM + r_in_tile]);
+                }
+                named_bar_arrive(2, kEW * 32);
+#pragma unroll
+                for (int pp = 0; pp < kParts - 1; ++pp) {
+                    if (ob1[pp] != -INFINITY) top3_merge_insert(t, ob1[pp], oi1[pp]);
+                    if (oi2[pp] >= 0) top3_merge_insert(t, ob2[pp], oi2[pp]);
+                    t.b3 = fmaxf(t.b3, ob3[pp]);
+                }
+
+                const bool valid = row < p.n_cand;
+                const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
+                const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
+                const bool flagged = valid && !p.no_recheck && (near_tie || near_thr);
+                const bool full = flagged && (t.b1 - t.b3 <= p.delta);
+                if (valid) {
+                    p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
+                    p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
+                    if (p.best_val != nullptr) p.best_val[row] = t.b1;
+                }
+                const bool pair = flagged && !full;
+                const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
+                const uint32_t umask = __ballot_sync(0xffffffffu, full);
+                if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
+                    int32_t slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->recheck_count, __popc(pmask));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (pair) {
+                        const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
+                        if (slot < p.lists.rec_cap) {
+                            RecheckRec r;
+                            r.row = static_cast<int32_t>(row);
+                            r.idx1 = t.i1;
+                            r.idx2 = near_tie ? t.i2 : -1;
+                            r.full = 0;
+                            p.lists.recs[slot] = r;
+                        }
+                    }
+                }
+                if (umask != 0) {                                  // ... and to the full-rescan list
+                    int32_t slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->full_count, __popc(umask));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (full) {
+                        const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
+                        if (slot < p.lists.full_cap) {
+                            p.lists.full_rows[slot] = static_cast<int32_t>(row);
+                            p.lists.full_keys[slot] = 0ull;
+                            if (slot % kFullGroup == 0) p.lists.full_ctr[slot / kFullGroup] = 0;
+                        }
                     }
                 }
             }
-            if (umask != 0) {                                  // ... and to the full-rescan list
-                int32_t slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&lists.hdr->full_count, __popc(umask));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (full) {
-                    const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
-                    if (slot < lists.full_cap) {
-                        lists.full_rows[slot] = static_cast<int32_t>(row);
-                        lists.full_keys[slot] = 0ull;
-                        if (slot % kFullGroup == 0) lists.full_ctr[slot / kFullGroup] = 0;
-                    }
-                }
-            }
+            first_tile = false;
         }
+        if (pr && lane == 0) {
+            p.prof[blockIdx.x * 16 + 10] = static_cast<unsigned long long>(clock64() - t_begin);
+            p.prof[blockIdx.x * 16 + 11] = w_tfull;
+        }
+        // balance the last bar.arrive(2) of the lower half so no barrier state is left pending
+        if (h != 0 && !first_tile) named_bar_sync(2, kEW * 32);
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (kCG == 2) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+        else          tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -325,6 +531,13 @@ int make_tmap(CUtensorMap* m, const __half* base, int64_t rows, int32_t ld, int3
     return FFR_OK;
 }
 
+unsigned long long* g_prof = nullptr;
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v) ? atoi(v) : dflt;
+}
+
 int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                            RecheckLists lists, int no_recheck, float* dbg_scores, cudaStream_t s) {
@@ -336,31 +549,62 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
         set_error("filter_mma: n_ref / n_cand must be < 2^31");
         return FFR_ERR_UNSUPPORTED;
     }
+    // tuning knobs (experiments only): FFR_CTA_GROUP=1|2, FFR_A_STAGES, FFR_B_STAGES
+    const int sms = num_sms();
+    // cta_group::2 pays off once the B stream dominates (measured: dim 512 +10%, dim <= 256 slower)
+    int cg = env_int("FFR_CTA_GROUP", dim_pad >= 384 ? 2 : 1);
+    if (cg != 2 || (sms & 1)) cg = 1;
     const int kb = dim_pad / kBlockK;
     const uint32_t a_stage = kb * kABlockBytes;
+    const uint32_t b_stage = (kTileN / cg) * kBlockK * 2;
     int a_stages = a_stage <= 32768 ? 3 : (a_stage <= 65536 ? 2 : 1);
-    const int64_t n_tiles = (n_cand + kTileM - 1) / kTileM;
-    const uint32_t budget = kSmemLimit - kBarrierBytes - 1024;   // 1024: alignment slack
-    int b_stages = static_cast<int>((budget - a_stages * a_stage) / kBStageBytes);
+    a_stages = env_int("FFR_A_STAGES", a_stages);
+    if (a_stages < 1) a_stages = 1;
+    if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+    const int ew = 8;      // 16 epilogue warps were measured: no gain (the TMEM read path, not latency, bounds pass 1)
+    const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
+    const uint32_t budget = kSmemLimit - extra;
+    while (a_stages > 1 && a_stages * a_stage + 2 * b_stage > budget) --a_stages;
+    if (a_stages * a_stage + 2 * b_stage > budget) { set_error("filter_mma: not enough shared memory for dim %d", dim_pad); return FFR_ERR_UNSUPPORTED; }
+    int b_stages = static_cast<int>((budget - a_stages * a_stage) / b_stage);
     if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-    if (b_stages < 2) { set_error("filter_mma: not enough shared memory for dim %d", dim_pad); return FFR_ERR_UNSUPPORTED; }
-    const uint32_t smem = a_stages * a_stage + b_stages * kBStageBytes + kBarrierBytes + 1024;
+    const int b_env = env_int("FFR_B_STAGES", 0);
+    if (b_env >= 2 && b_env < b_stages) b_stages = b_env;
+    const uint32_t smem = a_stages * a_stage + b_stages * b_stage + extra;
 
     CUtensorMap tm_c, tm_r;
     int rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
     if (rc != FFR_OK) return rc;
-    rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN);
+    rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN / cg);
     if (rc != FFR_OK) return rc;
 
+    KParams p;
+    p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
+    p.thr = thr; p.delta = delta; p.thr_band = thr_band; p.ref_index_base = ref_index_base;
+    p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
+
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
+    KernelFn fn = cg == 1 ? filter_mma_kernel<1, 8> : filter_mma_kernel<2, 8>;
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
-    const int sms = num_sms();
-    const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
-    filter_mma_kernel<<<grid, kThreads, smem, s>>>(tm_c, tm_r, n_ref, n_cand, kb, a_stages, b_stages, thr, delta, thr_band,
-                                                   ref_index_base, keep, idx, val, lists, no_recheck, dbg_scores);
+    const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);
+    const int64_t max_groups = sms / cg;
+    const unsigned grid = static_cast<unsigned>((n_tiles < max_groups ? n_tiles : max_groups) * cg);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(64 + 32 * ew);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tm_c, tm_r, p));
     FFR_LAUNCH_CHECK("filter_mma");
     return FFR_OK;
 }
@@ -373,6 +617,8 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, 
     return launch_filter_mma_impl(ref16, n_ref, cand16, n_cand, dim_pad, thr, delta, thr_band, ref_index_base, keep, idx, val,
                                   lists, no_recheck, nullptr, s);
 }
+
+void set_mma_prof_buffer(unsigned long long* dev_ptr) { g_prof = dev_ptr; }
 
 // test hook (not part of the ABI in include/ffr.h): additionally dumps the full score matrix
 int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,

@@ -16,6 +16,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kKC = 32;            // floats per staged reference chunk (128 B)
+constexpr int kKCPad = 36;         // padded row stride: conflict-free float4 reads, 16-byte aligned
 
 __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, const float* __restrict__ r, int32_t dim,
                                           float cc_sqrt, int lane, bool vec) {
@@ -142,40 +144,74 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
         int32_t bidx[kFullGroup];
 #pragma unroll
         for (int j = 0; j < kFullGroup; ++j) { best[j] = -INFINITY; bidx[j] = 0x7FFFFFFF; }
-        for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
-            float acc[kFullGroup];
+        if (kVec) {
+            // references are staged through shared memory in [kThreads refs] x [kKC floats] tiles with coalesced
+            // 128-byte row segments (8 threads per row), row stride kKCPad floats so that the thread-per-reference
+            // float4 reads below are bank-conflict free; the candidate chunk is a warp-wide broadcast read.
+            float* s_r = s_c + kFullGroup * dim;
+            const int n_kc = (dim + kKC - 1) / kKC;
+            for (int64_t i0 = lo; i0 < hi; i0 += kThreads) {
+                float acc[kFullGroup];
 #pragma unroll
-            for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
-            float rr = 0.f;
-            const float* r = ref + i * dim;
-            if (kVec) {
-                const float4* r4 = reinterpret_cast<const float4*>(r);
-                const float4* c4 = reinterpret_cast<const float4*>(s_c);
-                const int nv = dim >> 2;
-#pragma unroll 2
-                for (int k = 0; k < nv; ++k) {
-                    const float4 rv = __ldg(r4 + k);
-                    rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
+                for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
+                float rr = 0.f;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    __syncthreads();
 #pragma unroll
-                    for (int j = 0; j < kFullGroup; ++j) {
-                        const float4 cv = c4[j * nv + k];          // same address across the warp: broadcast
-                        acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
-                        acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
+                    for (int u = 0; u < (kKC / 4); ++u) {
+                        const int f = threadIdx.x + kThreads * u;
+                        const int rrow = f >> 3, c4 = f & 7;
+                        const int64_t gi = i0 + rrow;
+                        const int col = kc * kKC + c4 * 4;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (gi < hi && col < dim) v = __ldg(reinterpret_cast<const float4*>(ref + gi * dim + col));
+                        *reinterpret_cast<float4*>(s_r + rrow * kKCPad + c4 * 4) = v;
+                    }
+                    __syncthreads();
+                    const float4* r4 = reinterpret_cast<const float4*>(s_r + threadIdx.x * kKCPad);
+#pragma unroll
+                    for (int j4 = 0; j4 < kKC / 4; ++j4) {
+                        const int col = kc * kKC + j4 * 4;
+                        if (col >= dim) break;
+                        const float4 rv = r4[j4];
+                        rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
+#pragma unroll
+                        for (int j = 0; j < kFullGroup; ++j) {
+                            const float4 cv = *reinterpret_cast<const float4*>(s_c + j * dim + col);
+                            acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
+                            acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
+                        }
                     }
                 }
-            } else {
+                const int64_t i = i0 + threadIdx.x;
+                if (i < hi) {
+                    const float rs = __fsqrt_rn(rr);
+#pragma unroll
+                    for (int j = 0; j < kFullGroup; ++j) {
+                        const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
+                        if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
+                    }
+                }
+            }
+        } else {
+            for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+                float acc[kFullGroup];
+#pragma unroll
+                for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
+                float rr = 0.f;
+                const float* r = ref + i * dim;
                 for (int k = 0; k < dim; ++k) {
                     const float rv = __ldg(r + k);
                     rr = fmaf(rv, rv, rr);
 #pragma unroll
                     for (int j = 0; j < kFullGroup; ++j) acc[j] = fmaf(s_c[j * dim + k], rv, acc[j]);
                 }
-            }
-            const float rs = __fsqrt_rn(rr);
+                const float rs = __fsqrt_rn(rr);
 #pragma unroll
-            for (int j = 0; j < kFullGroup; ++j) {
-                const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
-                if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
+                for (int j = 0; j < kFullGroup; ++j) {
+                    const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
+                    if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
+                }
             }
         }
         // block merge: warp shuffle max on the packed key, then one atomicMax per (warp, row)
@@ -269,7 +305,13 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     if (gx > groups) gx = groups;
     if (gx < 1) gx = 1;
     const dim3 g2(static_cast<unsigned>(gx), static_cast<unsigned>(splits));
-    if (vec) rescan_full_kernel<true><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+    const size_t smem_full = smem + static_cast<size_t>(kThreads) * kKCPad * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FFR_CUDA_TRY(cudaFuncSetAttribute(rescan_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    if (vec) rescan_full_kernel<true><<<g2, kThreads, smem_full, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
                                                                   lists, band_tol, band_count, band_rows, band_cap);
     else     rescan_full_kernel<false><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
                                                                    lists, band_tol, band_count, band_rows, band_cap);

@@ -1,11 +1,9 @@
 #!/usr/bin/env python
 """GPU diagnostic: raw tcgen05 score tiles against a torch fp32 matmul of the same fp16 rows, then quick timings.
-Run on the GPU box:  python tools/diag_mma.py [--perf]"""
+Run on the GPU box:  [FFR_CTA_GROUP=2] python tools/diag_mma.py [--raw] [--perf] [--sweep] [--stream]"""
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,52 +36,94 @@ def raw(n_ref, n_cand, dim):
     e = torch.nan_to_num(err, nan=9.0)
     print(f"  [{n_ref}x{n_cand}x{dim}] nan={nan} max_err={e.max().item():.3e} mean_err={e.mean().item():.3e} "
           f"val_err={(val - want.max(1).values).abs().max().item():.3e} "
-          f"idx_match={(idx.long() == want.argmax(1)).float().mean().item():.4f}")
+          f"idx_match={(idx.long() == want.argmax(1)).float().mean().item():.4f}", flush=True)
     if e.max().item() > 1e-4:
         bad = (e > 1e-4)
-        rows = bad.any(1).nonzero().flatten()[:8].tolist()
+        rows = bad.any(1).nonzero().flatten()
         cols = bad.any(0).nonzero().flatten()
-        print("   bad rows (first 8):", rows, " bad cols: count", cols.numel(), "first", cols[:16].tolist())
-        print("   got[0,:8]", scores[0, :8].tolist())
-        print("   want[0,:8]", want[0, :8].tolist())
-        # does the result look like a permutation of K chunks / rows?
-        for shift in (8, 16, 32, 64):
-            if n_ref > shift:
-                print(f"   err vs want shifted by {shift} cols:", (scores[:, :-shift] - want[:, shift:]).abs().max().item())
+        print("   bad rows: count", rows.numel(), "first", rows[:8].tolist(), "last", rows[-4:].tolist(),
+              " bad cols: count", cols.numel(), "first", cols[:8].tolist(), "last", cols[-4:].tolist())
+        print("   got[0,:6]", scores[0, :6].tolist(), " want[0,:6]", want[0, :6].tolist())
+        r0 = rows[0].item()
+        print(f"   got[{r0},:6]", scores[r0, :6].tolist(), f" want[{r0},:6]", want[r0, :6].tolist())
         return False
     return True
 
 
-def perf(n_ref, n_cand, dim, flags=0, iters=5):
+def perf(n_ref, n_cand, dim, flags=0, iters=5, metric="cosine", thr=0.5):
     g = torch.Generator(device="cuda").manual_seed(2)
     ref = torch.nn.functional.normalize(torch.randn(n_ref, dim, device="cuda", generator=g))
     cand = torch.nn.functional.normalize(torch.randn(n_cand, dim, device="cuda", generator=g))
     cand[::2] = torch.nn.functional.normalize(ref[torch.randint(0, n_ref, (cand[::2].shape[0],), device="cuda")] * 0.8
                                               + cand[::2] * 0.6)
-    res = ops.face_filter(ref, cand, 0.5, flags=flags, want_stats=True)
+    res = ops.face_filter(ref, cand, thr, flags=flags, want_stats=True, metric=metric)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     ev[0].record()
     for i in range(iters):
-        ops.face_filter(ref, cand, 0.5, flags=flags, out=(res.keep, res.best_idx, res.best_val))
+        ops.face_filter(ref, cand, thr, flags=flags, out=(res.keep, res.best_idx, res.best_val), metric=metric)
         ev[i + 1].record()
     torch.cuda.synchronize()
     ms = min(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     pairs = n_ref * n_cand
-    print(f"  perf [{n_ref}x{n_cand}x{dim}] flags={flags}: {ms:.3f} ms  {pairs / ms / 1e6:.1f} Gpairs/s  "
-          f"{2 * pairs * dim / ms / 1e9:.1f} TFLOP/s  stats={res.stats} keep={res.keep.float().mean().item():.3f}")
+    tag = f"cg={os.environ.get('FFR_CTA_GROUP', '1')} A={os.environ.get('FFR_A_STAGES', '-')} B={os.environ.get('FFR_B_STAGES', '-')}"
+    print(f"  perf [{n_ref}x{n_cand}x{dim}] {metric} flags={flags} {tag}: {ms:.3f} ms  {pairs / ms / 1e6:.1f} Gpairs/s  "
+          f"{2 * pairs * dim / ms / 1e9:.1f} TFLOP/s  {n_cand * dim * 4 / ms / 1e6:.0f} GB/s(cand)  stats={res.stats} "
+          f"keep={res.keep.float().mean().item():.3f}", flush=True)
+
+
+def prof(n_ref, n_cand, dim):
+    """Where does K2's pipeline wait?  Stall cycles of the TMA thread, the MMA thread and one epilogue warp."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ref = torch.nn.functional.normalize(torch.randn(n_ref, dim, device="cuda", generator=g))
+    cand = torch.nn.functional.normalize(torch.randn(n_cand, dim, device="cuda", generator=g))
+    ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
+    buf = torch.zeros(160 * 16, dtype=torch.int64, device="cuda")
+    lib.ffr_debug_set_prof(buf.data_ptr())
+    ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
+    torch.cuda.synchronize()
+    lib.ffr_debug_set_prof(None)
+    b = buf.view(160, 16).double()
+    b = b[b[:, 0] > 0]
+    m = b.mean(0)
+    lead = b[b[:, 4] > 0]
+    ml = lead.mean(0)
+    tiles = ml[8].item()
+    print(f"  prof [{n_ref}x{n_cand}x{dim}] cg={os.environ.get('FFR_CTA_GROUP', '1')} ctas={b.shape[0]} (leaders {lead.shape[0]}), "
+          f"ref tiles per CTA {tiles:.0f}")
+    print(f"    TMA thread : total {m[0]:.3e} cyc; waiting a_empty {m[1] / m[0]:.1%}, b_empty {m[2] / m[0]:.1%}")
+    print(f"    MMA thread : total {ml[4]:.3e} cyc ({ml[4] / tiles:.0f} per ref tile); waiting a_full {ml[5] / ml[4]:.1%}, "
+          f"t_empty {ml[6] / ml[4]:.1%}, b_full {ml[7] / ml[4]:.1%}")
+    print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
+          f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
 
 
 if __name__ == "__main__":
-    print(torch.cuda.get_device_name(0), _lib.load().ffr_build_info().decode())
+    print(torch.cuda.get_device_name(0), _lib.load().ffr_build_info().decode(), "FFR_CTA_GROUP =", os.environ.get("FFR_CTA_GROUP"))
     ok = True
-    for shape in [(256, 128, 64), (256, 128, 128), (512, 256, 512), (100, 77, 128), (1000, 333, 192), (4096, 4096, 256)]:
-        ok = raw(*shape) and ok
-    print("RAW", "OK" if ok else "FAILED")
+    if "--raw" in sys.argv:
+        for shape in [(256, 128, 64), (256, 256, 128), (512, 256, 512), (100, 77, 128), (1000, 333, 192), (4096, 4096, 256)]:
+            ok = raw(*shape) and ok
+        print("RAW", "OK" if ok else "FAILED", flush=True)
     if "--perf" in sys.argv and ok:
         perf(1000, 100_000, 128)
         perf(1000, 100_000, 128, flags=ops.FLAG_NO_RECHECK)
         perf(10_000, 1_000_000, 512)
         perf(10_000, 1_000_000, 512, flags=ops.FLAG_NO_RECHECK)
         perf(100_000, 1_250_000, 128, flags=ops.FLAG_NO_RECHECK, iters=2)
-        perf(1, 10_000_000, 128)
+        perf(256, 2_000_000, 128, flags=ops.FLAG_NO_RECHECK)
+    if "--sweep" in sys.argv and ok:
+        for b in (2, 3, 4, 5, 6):
+            os.environ["FFR_B_STAGES"] = str(b)
+            perf(10_000, 500_000, 256, flags=ops.FLAG_NO_RECHECK, iters=3)
+        os.environ.pop("FFR_B_STAGES")
+    if "--prof" in sys.argv:
+        prof(10_000, 1_000_000, 512)
+        prof(10_000, 500_000, 256)
+        prof(100_000, 300_000, 128)
+        prof(1000, 100_000, 128)
+    if "--stream" in sys.argv:
+        perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
+        perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
+        perf(8, 10_000_000, 128)
