@@ -79,23 +79,47 @@ __device__ __forceinline__ void top3_merge_insert(Top3& t, float v, int32_t idx)
     t.b1 = g1 ? v : t.b1;
 }
 
-// v: 32 consecutive scores of this thread's candidate; base = reference index of v[0]
-__device__ __forceinline__ void process_chunk(const float (&v)[32], int32_t base, float delta, Top3& t) {
+// v: 32 consecutive scores of this thread's candidate; base = reference index of v[0].
+// gate = running best - delta (maintained here): a chunk / 8-column group whose maximum stays below the gate cannot
+// change the top-3 window and is skipped.  The skip is a plain per-thread branch: when no lane of the warp takes it
+// the warp falls through at the cost of one compare (no vote), and ptxas reconverges the warp at the end of the
+// block, before the next warp-wide tcgen05.ld.
+__device__ __forceinline__ void process_chunk(const float (&v)[32], int32_t base, float delta, Top3& t, float& gate) {
     float s[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         s[k] = fmax3(fmax3(v[8 * k + 0], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
                      fmaxf(v[8 * k + 6], v[8 * k + 7]));
     const float cmax = fmax3(s[0], s[1], fmaxf(s[2], s[3]));
-    if (__any_sync(0xffffffffu, cmax >= t.b1 - delta)) {
+    if (cmax >= gate) {
+        // After this chunk the window is [max(best, cmax) - delta, ...]; only columns inside it matter.  Nearly
+        // always that is the chunk maximum alone: one insertion, its column found from a 32-bit compare mask.
+        const float w = fmaxf(t.b1, cmax) - delta;
+        uint32_t ge = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (__any_sync(0xffffffffu, s[k] >= t.b1 - delta)) {
+        for (int j = 0; j < 32; ++j) ge |= (v[j] >= w) ? (1u << j) : 0u;
+        if ((ge & (ge - 1)) == 0) {
+            top3_insert(t, cmax, base + __ffs(ge) - 1);
+        } else {                                  // several columns inside the window: ordered insertion, 8 at a time
 #pragma unroll
-                for (int j = 0; j < 8; ++j) top3_insert(t, v[8 * k + j], base + 8 * k + j);
+            for (int k = 0; k < 4; ++k) {
+                if (s[k] >= w) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) top3_insert(t, v[8 * k + j], base + 8 * k + j);
+                }
             }
         }
+        gate = t.b1 - delta;
     }
+}
+
+__device__ __forceinline__ float chunk_max(const float (&v)[32]) {
+    float s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s[k] = fmax3(fmax3(v[8 * k + 0], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
+                     fmaxf(v[8 * k + 6], v[8 * k + 7]));
+    return fmax3(s[0], s[1], fmaxf(s[2], s[3]));
 }
 
 __device__ __forceinline__ void mask_chunk(float (&v)[32], int valid) {
@@ -355,6 +379,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             t.b1 = t.b2 = t.b3 = -INFINITY;
             t.i1 = 0;
             t.i2 = -1;
+            float gate = -INFINITY;                             // running best - delta
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
                 const uint32_t acc = t_it & 1, tph = (t_it >> 1) & 1;
@@ -380,8 +405,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         for (int j = 0; j < 32; ++j)
                             if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = va[j];
                     }
-                    if (p.epi_mode == 1) t.b1 = fmax3(t.b1, va[0], va[31]); else
-                    process_chunk(va, col0 + c * 32, p.delta, t);
+                    if (p.epi_mode == 1) t.b1 = fmax3(t.b1, va[0], va[31]); else if (p.epi_mode == 2) t.b1 = fmaxf(t.b1, chunk_max(va)); else
+                    process_chunk(va, col0 + c * 32, p.delta, t, gate);
                     if (c + 1 < c_end) {
                         tmem_ld_wait();
                         if (c + 2 < c_end) tmem_ld_32x32(taddr + (c + 2) * 32, va);
@@ -392,8 +417,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                                 if (col0 + (c + 1) * 32 + j < p.n_ref)
                                     p.dbg_scores[row * p.n_ref + col0 + (c + 1) * 32 + j] = vb[j];
                         }
-                        if (p.epi_mode == 1) t.b1 = fmax3(t.b1, vb[0], vb[31]); else
-                        process_chunk(vb, col0 + (c + 1) * 32, p.delta, t);
+                        if (p.epi_mode == 1) t.b1 = fmax3(t.b1, vb[0], vb[31]); else if (p.epi_mode == 2) t.b1 = fmaxf(t.b1, chunk_max(vb)); else
+                        process_chunk(vb, col0 + (c + 1) * 32, p.delta, t, gate);
                     }
                 }
                 tc_fence_before();
