@@ -106,28 +106,33 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
     idx = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFull));
 }
 
+// Work items are (group of kFullGroup flagged rows, slice of kSliceRefs references), handed out round-robin over a
+// fixed grid (the flagged-row count only exists on the device); n_slices slices merge into one result per row.
+constexpr int kSliceRefs = 512;
+
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
 rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
                    int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
                    float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
                    int64_t* band_rows, int64_t band_cap) {
-    extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows
+    extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows | staged reference tile
     __shared__ float s_ccs[kFullGroup];
     __shared__ unsigned long long s_key[kWarps][kFullGroup];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
-    const int splits = gridDim.y;
-    const int64_t per = (n_ref + splits - 1) / splits;
-    const int64_t lo = static_cast<int64_t>(blockIdx.y) * per;
-    const int64_t hi = (lo + per < n_ref) ? lo + per : n_ref;
+    const int64_t n_slices = (n_ref + kSliceRefs - 1) / kSliceRefs;
     const int64_t n_groups = (count + kFullGroup - 1) / kFullGroup;
-    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int64_t n_items = n_groups * n_slices;
+    int64_t parked = -1;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t g = item / n_slices, slice = item - g * n_slices;
+        const int64_t lo = slice * kSliceRefs;
+        const int64_t hi = (lo + kSliceRefs < n_ref) ? lo + kSliceRefs : n_ref;
         __syncthreads();
-        // warp w parks candidate row w of the group (kWarps == kFullGroup)
-        {
+        if (g != parked) {                                     // warp w parks candidate row w of the group
             const int64_t slot = g * kFullGroup + w;
             float cc = 0.f;
             if (slot < count) {
@@ -138,6 +143,7 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
             }
             cc = warp_sum(cc);
             if (lane == 0) s_ccs[w] = __fsqrt_rn(cc);
+            parked = g;
         }
         __syncthreads();
         float best[kFullGroup];
@@ -147,49 +153,66 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
         if (kVec) {
             // references are staged through shared memory in [kThreads refs] x [kKC floats] tiles with coalesced
             // 128-byte row segments (8 threads per row), row stride kKCPad floats so that the thread-per-reference
-            // float4 reads below are bank-conflict free; the candidate chunk is a warp-wide broadcast read.
+            // float4 reads are bank-conflict free; the candidate chunk is a warp-wide broadcast read.  The next
+            // tile chunk is prefetched into registers while the current one is consumed.
             float* s_r = s_c + kFullGroup * dim;
             const int n_kc = (dim + kKC - 1) / kKC;
-            for (int64_t i0 = lo; i0 < hi; i0 += kThreads) {
-                float acc[kFullGroup];
+            const int64_t n_rt = (hi - lo + kThreads - 1) / kThreads;
+            const int64_t n_it = n_rt * n_kc;
+            float4 pf[kKC / 4];
+            auto fetch = [&](int64_t it) {
+                const int64_t i0 = lo + (it / n_kc) * kThreads;
+                const int kc = static_cast<int>(it % n_kc);
 #pragma unroll
-                for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
-                float rr = 0.f;
-                for (int kc = 0; kc < n_kc; ++kc) {
-                    __syncthreads();
-#pragma unroll
-                    for (int u = 0; u < (kKC / 4); ++u) {
-                        const int f = threadIdx.x + kThreads * u;
-                        const int rrow = f >> 3, c4 = f & 7;
-                        const int64_t gi = i0 + rrow;
-                        const int col = kc * kKC + c4 * 4;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (gi < hi && col < dim) v = __ldg(reinterpret_cast<const float4*>(ref + gi * dim + col));
-                        *reinterpret_cast<float4*>(s_r + rrow * kKCPad + c4 * 4) = v;
-                    }
-                    __syncthreads();
-                    const float4* r4 = reinterpret_cast<const float4*>(s_r + threadIdx.x * kKCPad);
-#pragma unroll
-                    for (int j4 = 0; j4 < kKC / 4; ++j4) {
-                        const int col = kc * kKC + j4 * 4;
-                        if (col >= dim) break;
-                        const float4 rv = r4[j4];
-                        rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
-#pragma unroll
-                        for (int j = 0; j < kFullGroup; ++j) {
-                            const float4 cv = *reinterpret_cast<const float4*>(s_c + j * dim + col);
-                            acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
-                            acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
-                        }
-                    }
+                for (int u = 0; u < (kKC / 4); ++u) {
+                    const int f = threadIdx.x + kThreads * u;
+                    const int64_t gi = i0 + (f >> 3);
+                    const int col = kc * kKC + (f & 7) * 4;
+                    pf[u] = (gi < hi && col < dim) ? __ldg(reinterpret_cast<const float4*>(ref + gi * dim + col))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                const int64_t i = i0 + threadIdx.x;
-                if (i < hi) {
-                    const float rs = __fsqrt_rn(rr);
+            };
+            fetch(0);
+            float acc[kFullGroup];
+            float rr = 0.f;
+            for (int64_t it = 0; it < n_it; ++it) {
+                const int kc = static_cast<int>(it % n_kc);
+                if (kc == 0) {
+#pragma unroll
+                    for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
+                    rr = 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < (kKC / 4); ++u) {
+                    const int f = threadIdx.x + kThreads * u;
+                    *reinterpret_cast<float4*>(s_r + (f >> 3) * kKCPad + (f & 7) * 4) = pf[u];
+                }
+                __syncthreads();
+                if (it + 1 < n_it) fetch(it + 1);
+                const float4* r4 = reinterpret_cast<const float4*>(s_r + threadIdx.x * kKCPad);
+#pragma unroll
+                for (int j4 = 0; j4 < kKC / 4; ++j4) {
+                    const int col = kc * kKC + j4 * 4;
+                    if (col >= dim) break;
+                    const float4 rv = r4[j4];
+                    rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
 #pragma unroll
                     for (int j = 0; j < kFullGroup; ++j) {
-                        const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
-                        if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
+                        const float4 cv = *reinterpret_cast<const float4*>(s_c + j * dim + col);
+                        acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
+                        acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
+                    }
+                }
+                if (kc == n_kc - 1) {
+                    const int64_t i = lo + (it / n_kc) * kThreads + threadIdx.x;
+                    if (i < hi) {
+                        const float rs = __fsqrt_rn(rr);
+#pragma unroll
+                        for (int j = 0; j < kFullGroup; ++j) {
+                            const float sc = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
+                            if (sc > best[j]) { best[j] = sc; bidx[j] = static_cast<int32_t>(i); }
+                        }
                     }
                 }
             }
@@ -209,12 +232,12 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
                 const float rs = __fsqrt_rn(rr);
 #pragma unroll
                 for (int j = 0; j < kFullGroup; ++j) {
-                    const float s = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
-                    if (s > best[j]) { best[j] = s; bidx[j] = static_cast<int32_t>(i); }
+                    const float sc = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
+                    if (sc > best[j]) { best[j] = sc; bidx[j] = static_cast<int32_t>(i); }
                 }
             }
         }
-        // block merge: warp shuffle max on the packed key, then one atomicMax per (warp, row)
+        // block merge: warp shuffle max on the packed key, then one atomicMax per row
 #pragma unroll
         for (int j = 0; j < kFullGroup; ++j) {
             unsigned long long key = (bidx[j] == 0x7FFFFFFF) ? 0ull : pack_key(best[j], bidx[j]);
@@ -235,7 +258,7 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
         }
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&lists.full_ctr[g], 1) == splits - 1) ? 1 : 0;
+        if (threadIdx.x == 0) s_last = (atomicAdd(&lists.full_ctr[g], 1) == static_cast<int>(n_slices) - 1) ? 1 : 0;
         __syncthreads();
         if (s_last && threadIdx.x < kFullGroup) {
             __threadfence();
@@ -296,15 +319,13 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
                                                                              idx, val, lists, band_tol, band_count,
                                                                              band_rows, band_cap, vec);
     FFR_LAUNCH_CHECK("recheck_pairs");
-    // full rescans: slice the reference axis so that even a handful of rows spreads over the chip
-    int splits = static_cast<int>(n_ref / 2048);
-    if (splits < 1) splits = 1;
-    if (splits > 32) splits = 32;
-    int64_t groups = (n_cand + kFullGroup - 1) / kFullGroup;
-    int64_t gx = (static_cast<int64_t>(sms) * 4 + splits - 1) / splits;
-    if (gx > groups) gx = groups;
+    // full rescans: (row group, 512-reference slice) work items round-robin over a fixed grid
+    const int64_t groups = (n_cand + kFullGroup - 1) / kFullGroup;
+    const int64_t items = groups * ((n_ref + kSliceRefs - 1) / kSliceRefs);
+    int64_t gx = static_cast<int64_t>(sms) * 3;
+    if (gx > items) gx = items;
     if (gx < 1) gx = 1;
-    const dim3 g2(static_cast<unsigned>(gx), static_cast<unsigned>(splits));
+    const dim3 g2(static_cast<unsigned>(gx));
     const size_t smem_full = smem + static_cast<size_t>(kThreads) * kKCPad * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
