@@ -94,6 +94,7 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int32_t base
     if (cmax >= gate) {
         // After this chunk the window is [max(best, cmax) - delta, ...]; only columns inside it matter.  Nearly
         // always that is the chunk maximum alone: one insertion, its column found from a 32-bit compare mask.
+        // (Measured alternatives that were slower: warp votes instead of the per-thread branch; per-8-column masks.)
         const float w = fmaxf(t.b1, cmax) - delta;
         uint32_t ge = 0;
 #pragma unroll
@@ -205,7 +206,7 @@ struct KParams {
 };
 
 // kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8|16) = 4 TMEM lane quadrants x kEW/4 column parts.
-template <int kCG, int kEW>
+template <int kCG, int kEW, bool kX64>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const KParams p) {
@@ -394,6 +395,37 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 // stream this warp's column part out of TMEM chunk by chunk: the next chunk's tcgen05.ld is in flight
                 // while the current one is reduced.  (Measured alternatives that were slower: 16 epilogue warps; loading
                 // the whole part before reducing; a reduce-only first pass that re-reads flagged chunks.)
+                if constexpr (kX64) {
+                    // 64-column tcgen05.ld variant: half as many load / wait round trips per part
+                    float wa[64], wb[64];
+                    const int g_beg = c_beg >> 1, g_end = (c_end + 1) >> 1;
+                    auto handle = [&](float (&wv)[64], int g) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float (&v32)[32] = *reinterpret_cast<float (*)[32]>(&wv[32 * hh]);
+                            const int c = 2 * g + hh;
+                            if (c >= c_end) continue;
+                            if (ncols - c * 32 < 32) mask_chunk(v32, ncols - c * 32);
+                            if (p.dbg_scores != nullptr && row < p.n_cand) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = v32[j];
+                            }
+                            process_chunk(v32, col0 + c * 32, p.delta, t, gate);
+                        }
+                    };
+                    if (g_beg < g_end) tmem_ld_32x64(taddr + g_beg * 64, wa);
+                    for (int g = g_beg; g < g_end; g += 2) {
+                        tmem_ld_wait();
+                        if (g + 1 < g_end) tmem_ld_32x64(taddr + (g + 1) * 64, wb);
+                        handle(wa, g);
+                        if (g + 1 < g_end) {
+                            tmem_ld_wait();
+                            if (g + 2 < g_end) tmem_ld_32x64(taddr + (g + 2) * 64, wa);
+                            handle(wb, g + 1);
+                        }
+                    }
+                } else {
                 float va[32], vb[32];
                 if (c_beg < c_end) tmem_ld_32x32(taddr + c_beg * 32, va);
                 for (int c = c_beg; c < c_end; c += 2) {
@@ -420,6 +452,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (p.epi_mode == 1) t.b1 = fmax3(t.b1, vb[0], vb[31]); else if (p.epi_mode == 2) t.b1 = fmaxf(t.b1, chunk_max(vb)); else
                         process_chunk(vb, col0 + (c + 1) * 32, p.delta, t, gate);
                     }
+                }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -609,11 +642,15 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-    KernelFn fn = cg == 1 ? filter_mma_kernel<1, 8> : filter_mma_kernel<2, 8>;
+    const bool x64 = env_int("FFR_EPI_X64", 0) != 0;
+    KernelFn fn = cg == 1 ? (x64 ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)
+                          : (x64 ? filter_mma_kernel<2, 8, true> : filter_mma_kernel<2, 8, false>);
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);
