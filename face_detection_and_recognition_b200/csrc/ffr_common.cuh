@@ -36,7 +36,7 @@ struct RecheckRec {
     int32_t row;        // candidate row (local)
     int32_t idx1;       // best reference (local index), fp16-score space
     int32_t idx2;       // runner-up reference, or -1
-    int32_t full;       // 1: a third score was within delta -> full fp32 rescan
+    int32_t idx3;       // third reference inside the window, or -1
 };
 
 // rows whose third-best score is also within delta: rescanned against every reference in fp32 (K3b).

@@ -50,16 +50,19 @@ constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-bl
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;                       // 227 KiB opt-in maximum
 constexpr uint32_t kBarrierBytes = 512;                       // mbarriers + TMEM slot
-constexpr uint32_t kMergeBytes = kTileM * 5 * 4;              // top-3 hand-over of the upper column half
+constexpr uint32_t kMergeBytes = kTileM * 7 * 4;              // top-4 hand-over of the upper column half
 // per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
+// running top-4 scores of one candidate (first three with their reference index): what K3 needs to decide in fp32
 struct Top3 {
-    float b1, b2, b3;
-    int32_t i1, i2;
+    float b1, b2, b3, b4;
+    int32_t i1, i2, i3;
 };
 
 __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
-    const bool g1 = v > t.b1, g2 = v > t.b2, g3 = v > t.b3;
+    const bool g1 = v > t.b1, g2 = v > t.b2, g3 = v > t.b3, g4 = v > t.b4;
+    t.b4 = g3 ? t.b3 : (g4 ? v : t.b4);
+    t.i3 = g2 ? t.i2 : (g3 ? idx : t.i3);
     t.b3 = g2 ? t.b2 : (g3 ? v : t.b3);
     t.i2 = g1 ? t.i1 : (g2 ? idx : t.i2);
     t.b2 = g1 ? t.b1 : (g2 ? v : t.b2);
@@ -71,7 +74,10 @@ __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
 __device__ __forceinline__ void top3_merge_insert(Top3& t, float v, int32_t idx) {
     const bool g1 = (v > t.b1) || (v == t.b1 && idx < t.i1);
     const bool g2 = (v > t.b2) || (v == t.b2 && idx < t.i2);
-    const bool g3 = v > t.b3;
+    const bool g3 = (v > t.b3) || (v == t.b3 && idx < t.i3);
+    const bool g4 = v > t.b4;
+    t.b4 = g3 ? t.b3 : (g4 ? v : t.b4);
+    t.i3 = g2 ? t.i2 : (g3 ? idx : t.i3);
     t.b3 = g2 ? t.b2 : (g3 ? v : t.b3);
     t.i2 = g1 ? t.i1 : (g2 ? idx : t.i2);
     t.b2 = g1 ? t.b1 : (g2 ? v : t.b2);
@@ -226,7 +232,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][5][kTileM]
+    float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -377,9 +383,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
-            t.b1 = t.b2 = t.b3 = -INFINITY;
+            t.b1 = t.b2 = t.b3 = t.b4 = -INFINITY;
             t.i1 = 0;
-            t.i2 = -1;
+            t.i2 = t.i3 = -1;
             float gate = -INFINITY;                             // running best - delta
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
@@ -464,40 +470,43 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             }
             // ---- hand the upper column parts over, merge, emit (named barriers 1/2 among the epilogue threads)
             if (h != 0) {
-                float* mg = merge + (h - 1) * 5 * kTileM;
+                float* mg = merge + (h - 1) * 7 * kTileM;
                 if (!first_tile) named_bar_sync(2, kEW * 32);                  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
                 mg[2 * kTileM + r_in_tile] = t.b3;
-                mg[3 * kTileM + r_in_tile] = __int_as_float(t.i1);
-                mg[4 * kTileM + r_in_tile] = __int_as_float(t.i2);
+                mg[3 * kTileM + r_in_tile] = t.b4;
+                mg[4 * kTileM + r_in_tile] = __int_as_float(t.i1);
+                mg[5 * kTileM + r_in_tile] = __int_as_float(t.i2);
+                mg[6 * kTileM + r_in_tile] = __int_as_float(t.i3);
                 __threadfence_block();
                 named_bar_arrive(1, kEW * 32);
             } else {
                 named_bar_sync(1, kEW * 32);
-                float ob1[kParts - 1], ob2[kParts - 1], ob3[kParts - 1];
-                int32_t oi1[kParts - 1], oi2[kParts - 1];
+                float ob[kParts - 1][4];
+                int32_t oi[kParts - 1][3];
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    const float* mg = merge + pp * 5 * kTileM;
-                    ob1[pp] = mg[0 * kTileM + r_in_tile]; ob2[pp] = mg[1 * kTileM + r_in_tile];
-                    ob3[pp] = mg[2 * kTileM + r_in_tile];
-                    oi1[pp] = __float_as_int(mg[3 * kTileM + r_in_tile]);
-                    oi2[pp] = __float_as_int(mg[4 * kTileM + r_in_tile]);
+                    const float* mg = merge + pp * 7 * kTileM;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) oi[pp][e] = __float_as_int(mg[(4 + e) * kTileM + r_in_tile]);
                 }
                 named_bar_arrive(2, kEW * 32);
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    if (ob1[pp] != -INFINITY) top3_merge_insert(t, ob1[pp], oi1[pp]);
-                    if (oi2[pp] >= 0) top3_merge_insert(t, ob2[pp], oi2[pp]);
-                    t.b3 = fmaxf(t.b3, ob3[pp]);
+                    if (ob[pp][0] != -INFINITY) top3_merge_insert(t, ob[pp][0], oi[pp][0]);
+                    if (oi[pp][1] >= 0) top3_merge_insert(t, ob[pp][1], oi[pp][1]);
+                    if (oi[pp][2] >= 0) top3_merge_insert(t, ob[pp][2], oi[pp][2]);
+                    t.b4 = fmaxf(t.b4, ob[pp][3]);
                 }
 
                 const bool valid = row < p.n_cand;
                 const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
                 const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
                 const bool flagged = valid && !p.no_recheck && (near_tie || near_thr);
-                const bool full = flagged && (t.b1 - t.b3 <= p.delta);
+                const bool full = flagged && (t.b1 - t.b4 <= p.delta);     // four or more inside the window: full rescan
                 if (valid) {
                     p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
                     p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
@@ -517,7 +526,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             r.row = static_cast<int32_t>(row);
                             r.idx1 = t.i1;
                             r.idx2 = near_tie ? t.i2 : -1;
-                            r.full = 0;
+                            r.idx3 = (near_tie && t.i3 >= 0 && t.b1 - t.b3 <= p.delta) ? t.i3 : -1;
                             p.lists.recs[slot] = r;
                         }
                     }

@@ -16,8 +16,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKC = 32;            // floats per staged reference chunk (128 B)
-constexpr int kKCPad = 36;         // padded row stride: conflict-free float4 reads, 16-byte aligned
+constexpr int kKC = 8;             // floats per staged reference chunk (two float4)
+constexpr int kKCPad = 12;         // padded row stride (48 B): conflict-free float4 reads, 16-byte aligned
+constexpr int kRefsPerThread = 4;  // register tile: 4 references x kFullGroup candidates per thread
+constexpr int kTileRefs = kThreads * kRefsPerThread;   // 1024 references staged per tile
 
 __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, const float* __restrict__ r, int32_t dim,
                                           float cc_sqrt, int lane, bool vec) {
@@ -82,6 +84,10 @@ recheck_pairs_kernel(const float* __restrict__ ref, const float* __restrict__ ca
             const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec != 0);
             if (s2 > best || (s2 == best && rec.idx2 < bi)) { best = s2; bi = rec.idx2; }
         }
+        if (rec.idx3 >= 0) {
+            const float s3 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx3) * dim, dim, cc_sqrt, lane, vec != 0);
+            if (s3 > best || (s3 == best && rec.idx3 < bi)) { best = s3; bi = rec.idx3; }
+        }
         if (lane == 0)
             emit_result(rec.row, best, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
                         band_rows, band_cap);
@@ -108,7 +114,7 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
 
 // Work items are (group of kFullGroup flagged rows, slice of kSliceRefs references), handed out round-robin over a
 // fixed grid (the flagged-row count only exists on the device); n_slices slices merge into one result per row.
-constexpr int kSliceRefs = 512;
+constexpr int kSliceRefs = 1024;
 
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
@@ -151,70 +157,89 @@ rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
 #pragma unroll
         for (int j = 0; j < kFullGroup; ++j) { best[j] = -INFINITY; bidx[j] = 0x7FFFFFFF; }
         if (kVec) {
-            // references are staged through shared memory in [kThreads refs] x [kKC floats] tiles with coalesced
-            // 128-byte row segments (8 threads per row), row stride kKCPad floats so that the thread-per-reference
-            // float4 reads are bank-conflict free; the candidate chunk is a warp-wide broadcast read.  The next
-            // tile chunk is prefetched into registers while the current one is consumed.
+            // References are staged through shared memory in [kTileRefs refs] x [kKC floats] tiles (row stride kKCPad
+            // floats: the float4 reads of 8 consecutive threads hit 8 disjoint bank groups), the next tile chunk is
+            // prefetched into registers while the current one is consumed, and every thread owns a register tile of
+            // kRefsPerThread references (t, t + 256, ...) x kFullGroup candidates: per 8 K-values it issues 8 + 16
+            // shared loads for 256 FMAs (the candidate loads are warp-wide broadcasts).
             float* s_r = s_c + kFullGroup * dim;
             const int n_kc = (dim + kKC - 1) / kKC;
-            const int64_t n_rt = (hi - lo + kThreads - 1) / kThreads;
+            const int64_t n_rt = (hi - lo + kTileRefs - 1) / kTileRefs;
             const int64_t n_it = n_rt * n_kc;
-            float4 pf[kKC / 4];
-            auto fetch = [&](int64_t it) {
-                const int64_t i0 = lo + (it / n_kc) * kThreads;
-                const int kc = static_cast<int>(it % n_kc);
+            constexpr int kPf = kTileRefs * (kKC / 4) / kThreads;          // float4 per thread per chunk (8)
+            float4 pf[kPf];
+            auto fetch = [&](int64_t rt, int kc) {
+                const int64_t i0 = lo + rt * kTileRefs;
 #pragma unroll
-                for (int u = 0; u < (kKC / 4); ++u) {
-                    const int f = threadIdx.x + kThreads * u;
-                    const int64_t gi = i0 + (f >> 3);
-                    const int col = kc * kKC + (f & 7) * 4;
+                for (int u = 0; u < kPf; ++u) {
+                    const int f = threadIdx.x + kThreads * u;              // 2 float4 per reference row
+                    const int64_t gi = i0 + (f >> 1);
+                    const int col = kc * kKC + (f & 1) * 4;
                     pf[u] = (gi < hi && col < dim) ? __ldg(reinterpret_cast<const float4*>(ref + gi * dim + col))
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            fetch(0);
-            float acc[kFullGroup];
-            float rr = 0.f;
+            fetch(0, 0);
+            float acc[kRefsPerThread][kFullGroup];
+            float rr[kRefsPerThread];
+            int64_t rt = 0;
+            int kc = 0;
             for (int64_t it = 0; it < n_it; ++it) {
-                const int kc = static_cast<int>(it % n_kc);
                 if (kc == 0) {
 #pragma unroll
-                    for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
-                    rr = 0.f;
+                    for (int r = 0; r < kRefsPerThread; ++r) {
+                        rr[r] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < kFullGroup; ++j) acc[r][j] = 0.f;
+                    }
                 }
                 __syncthreads();
 #pragma unroll
-                for (int u = 0; u < (kKC / 4); ++u) {
+                for (int u = 0; u < kPf; ++u) {
                     const int f = threadIdx.x + kThreads * u;
-                    *reinterpret_cast<float4*>(s_r + (f >> 3) * kKCPad + (f & 7) * 4) = pf[u];
+                    *reinterpret_cast<float4*>(s_r + (f >> 1) * kKCPad + (f & 1) * 4) = pf[u];
                 }
                 __syncthreads();
-                if (it + 1 < n_it) fetch(it + 1);
-                const float4* r4 = reinterpret_cast<const float4*>(s_r + threadIdx.x * kKCPad);
+                int nkc = kc + 1;
+                int64_t nrt = rt;
+                if (nkc == n_kc) { nkc = 0; ++nrt; }
+                if (it + 1 < n_it) fetch(nrt, nkc);
 #pragma unroll
                 for (int j4 = 0; j4 < kKC / 4; ++j4) {
                     const int col = kc * kKC + j4 * 4;
-                    if (col >= dim) break;
-                    const float4 rv = r4[j4];
-                    rr = fmaf(rv.x, rv.x, rr); rr = fmaf(rv.y, rv.y, rr); rr = fmaf(rv.z, rv.z, rr); rr = fmaf(rv.w, rv.w, rr);
+                    if (col < dim) {
+                        float4 cv[kFullGroup];
 #pragma unroll
-                    for (int j = 0; j < kFullGroup; ++j) {
-                        const float4 cv = *reinterpret_cast<const float4*>(s_c + j * dim + col);
-                        acc[j] = fmaf(cv.x, rv.x, acc[j]); acc[j] = fmaf(cv.y, rv.y, acc[j]);
-                        acc[j] = fmaf(cv.z, rv.z, acc[j]); acc[j] = fmaf(cv.w, rv.w, acc[j]);
-                    }
-                }
-                if (kc == n_kc - 1) {
-                    const int64_t i = lo + (it / n_kc) * kThreads + threadIdx.x;
-                    if (i < hi) {
-                        const float rs = __fsqrt_rn(rr);
+                        for (int j = 0; j < kFullGroup; ++j) cv[j] = *reinterpret_cast<const float4*>(s_c + j * dim + col);
 #pragma unroll
-                        for (int j = 0; j < kFullGroup; ++j) {
-                            const float sc = __fdiv_rn(acc[j], __fmul_rn(rs, s_ccs[j]));
-                            if (sc > best[j]) { best[j] = sc; bidx[j] = static_cast<int32_t>(i); }
+                        for (int r = 0; r < kRefsPerThread; ++r) {
+                            const float4 rv = *reinterpret_cast<const float4*>(s_r + (threadIdx.x + r * kThreads) * kKCPad + j4 * 4);
+                            rr[r] = fmaf(rv.x, rv.x, rr[r]); rr[r] = fmaf(rv.y, rv.y, rr[r]);
+                            rr[r] = fmaf(rv.z, rv.z, rr[r]); rr[r] = fmaf(rv.w, rv.w, rr[r]);
+#pragma unroll
+                            for (int j = 0; j < kFullGroup; ++j) {
+                                acc[r][j] = fmaf(cv[j].x, rv.x, acc[r][j]); acc[r][j] = fmaf(cv[j].y, rv.y, acc[r][j]);
+                                acc[r][j] = fmaf(cv[j].z, rv.z, acc[r][j]); acc[r][j] = fmaf(cv[j].w, rv.w, acc[r][j]);
+                            }
                         }
                     }
                 }
+                if (kc == n_kc - 1) {
+#pragma unroll
+                    for (int r = 0; r < kRefsPerThread; ++r) {                    // ascending reference index per thread
+                        const int64_t i = lo + rt * kTileRefs + threadIdx.x + r * kThreads;
+                        if (i < hi) {
+                            const float rs = __fsqrt_rn(rr[r]);
+#pragma unroll
+                            for (int j = 0; j < kFullGroup; ++j) {
+                                const float sc = __fdiv_rn(acc[r][j], __fmul_rn(rs, s_ccs[j]));
+                                if (sc > best[j]) { best[j] = sc; bidx[j] = static_cast<int32_t>(i); }
+                            }
+                        }
+                    }
+                }
+                kc = nkc;
+                rt = nrt;
             }
         } else {
             for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
@@ -322,11 +347,11 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     // full rescans: (row group, 512-reference slice) work items round-robin over a fixed grid
     const int64_t groups = (n_cand + kFullGroup - 1) / kFullGroup;
     const int64_t items = groups * ((n_ref + kSliceRefs - 1) / kSliceRefs);
-    int64_t gx = static_cast<int64_t>(sms) * 3;
+    int64_t gx = static_cast<int64_t>(sms) * 2;               // two blocks per SM are resident (registers): one wave
     if (gx > items) gx = items;
     if (gx < 1) gx = 1;
     const dim3 g2(static_cast<unsigned>(gx));
-    const size_t smem_full = smem + static_cast<size_t>(kThreads) * kKCPad * sizeof(float);
+    const size_t smem_full = smem + static_cast<size_t>(kTileRefs) * kKCPad * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         FFR_CUDA_TRY(cudaFuncSetAttribute(rescan_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
