@@ -132,7 +132,9 @@ def cpu_port_rate(n_ref, dim, n_sample, seconds_target=None, threads=None):
     import numpy as np
     import torch
     from oracle import oracle
-    threads = threads or torch.get_num_threads()
+    if threads is None:                       # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
     rng = np.random.default_rng(42)
     ref = rng.standard_normal((n_ref, dim), dtype=np.float32)
     probe = rng.standard_normal((min(2048, n_sample), dim), dtype=np.float32)
@@ -157,7 +159,7 @@ def cpu_port_rate(n_ref, dim, n_sample, seconds_target=None, threads=None):
                 n_sample=n_sample, seconds=t_torch)
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU arithmetic for this path (oracle port; the reference is pure Python/NumPy and
     its TensorFlow front end cannot run here, so there is no oracle/_ref) on the host cores, same config and metric."""
     if rank != 0:
@@ -184,7 +186,7 @@ def run_reference(args, rank, world):
     sample = (f"{n_sample} of {w['n_cand']} candidates per step x all {n_ref} references x {dim}-d, vectorised fp32 "
               f"restatement ({'torch-CPU' if fn is oracle.filter_cosine_torch else 'NumPy'} sgemm + max/argmax + threshold), "
               f"{cores} threads; literal per-pair Python loop = {probe['literal_loop']:.3g} pairs/s on 1 thread")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "face pairs compared/sec (ref x cand cosine+filter)", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -193,7 +195,7 @@ def run_reference(args, rank, world):
                    "metric": "cosine"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -208,8 +210,20 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_rank()
+    # the contract is ONE JSON line on stdout: anything libraries print while we run (NCCL's version banner, warnings)
+    # is sent to stderr by pointing fd 1 at fd 2 until the result line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
 
     import torch
     import torch.distributed as dist
@@ -350,7 +364,7 @@ def main():
                            f"({cb['seconds']:.1f} s): vectorised fp32 oracle, torch-CPU {cb['torch_cpu']:.3g} / NumPy "
                            f"{cb['numpy']:.3g} pairs/s on {cb['threads']} threads; the reference's literal per-pair Python "
                            f"loop: {cb['literal_loop']:.3g} pairs/s on 1 thread")}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
