@@ -42,6 +42,8 @@ SIGNATURES = {
                                 _f32, _vp, _vp, _i64, C.c_int, _vp, _sz, _vp]),
     "ffr_filter_stats": (C.c_int, [_vp, C.POINTER(_i64), _vp]),
     "ffr_ref_mean_and_thres": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "ffr_ref_mean_and_thres_batched": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ffr_first_match_stream": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, C.c_int, _f32, _f32, _vp, _vp]),
     "ffr_ctx_create": (C.c_int, [C.c_int, _i64, _i64, _i32, C.POINTER(_vp)]),
     "ffr_ctx_destroy": (None, [_vp]),
     "ffr_ctx_filter_host": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, C.c_int, _f32, _i64, _vp, _vp, _vp, C.c_int]),

@@ -272,6 +272,28 @@ int ffr_ref_mean_and_thres(const float* ref_feat, int32_t n_ref, int32_t dim, fl
     return launch_ref_stats(ref_feat, n_ref, dim, mean, thres, static_cast<cudaStream_t>(stream));
 }
 
+int ffr_ref_mean_and_thres_batched(const float* ref_feat, const int32_t* offsets, int32_t n_classes, int32_t dim,
+                                   float* mean, float* thres, ffr_stream_t stream) {
+    if (n_classes < 0 || dim <= 0 || dim > 8192) { set_error("ref_mean_and_thres_batched: need n_classes >= 0, 0 < dim <= 8192"); return FFR_ERR_INVALID; }
+    if (n_classes == 0) return FFR_OK;
+    if (ref_feat == nullptr || offsets == nullptr || mean == nullptr || thres == nullptr) { set_error("ref_mean_and_thres_batched: null argument"); return FFR_ERR_INVALID; }
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    return launch_ref_stats_batched(ref_feat, offsets, n_classes, dim, mean, thres, static_cast<cudaStream_t>(stream));
+}
+
+int ffr_first_match_stream(float* gallery_feat, float* gallery_bbox, int32_t* gallery_count, int32_t capacity,
+                           const float* queries, const float* query_bbox, int32_t n_queries, int32_t dim, int metric,
+                           float normal_thres, float harsh_thres, int32_t* match_idx, ffr_stream_t stream) {
+    if (capacity <= 0 || n_queries < 0 || dim <= 0 || dim > 8192) { set_error("first_match_stream: need capacity > 0, n_queries >= 0, 0 < dim <= 8192"); return FFR_ERR_INVALID; }
+    if (metric != FFR_METRIC_COSINE && metric != FFR_METRIC_EUCLID) { set_error("unknown metric %d", metric); return FFR_ERR_INVALID; }
+    if (n_queries == 0) return FFR_OK;
+    if (gallery_feat == nullptr || gallery_count == nullptr || queries == nullptr || match_idx == nullptr ||
+        (query_bbox != nullptr && gallery_bbox == nullptr)) { set_error("first_match_stream: null argument"); return FFR_ERR_INVALID; }
+    if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
+    return launch_first_match_stream(gallery_feat, gallery_bbox, gallery_count, capacity, queries, query_bbox, n_queries, dim,
+                                     metric, normal_thres, harsh_thres, match_idx, static_cast<cudaStream_t>(stream));
+}
+
 // test hook (not in the public header): tcgen05 kernel on fp16 rows, dumping every score
 int ffr_debug_mma_scores(const void* ref16, int64_t n_ref, const void* cand16, int64_t n_cand, int32_t dim_pad,
                          float thr, uint8_t* keep, int32_t* idx, float* val, float* scores, void* workspace,

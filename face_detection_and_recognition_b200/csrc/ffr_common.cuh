@@ -231,6 +231,11 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
                    const float* ref_norm, const float* cand_norm, float thr, int64_t ref_index_base,
                    uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                    float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
+int launch_ref_stats_batched(const float* ref_feat, const int32_t* offsets, int32_t n_classes, int32_t dim, float* mean,
+                             float* thres, cudaStream_t s);
+int launch_first_match_stream(float* g_feat, float* g_bbox, int32_t* g_count, int32_t cap, const float* queries,
+                              const float* qboxes, int32_t n_queries, int32_t dim, int metric, float normal_thres,
+                              float harsh_thres, int32_t* match_idx, cudaStream_t s);
 void set_mma_prof_buffer(unsigned long long* dev_ptr);   // diagnostics: [grid][16] stall-cycle counters of K2
 int launch_ref_stats(const float* ref_feat, int32_t n_ref, int32_t dim, float* mean, float* thres, cudaStream_t s);
 int launch_pack_results(const uint8_t* keep, const int32_t* idx, int64_t m, int64_t m_pad, uint8_t* packed,

@@ -115,6 +115,20 @@ def _embed_paths(model, paths: List[str], batch_size: int) -> np.ndarray:
     return np.concatenate(outs, axis=0) if outs else np.zeros((0, 0), dtype=np.float32)
 
 
+def _embed_paths_device(model, paths: List[str], batch_size: int, device: torch.device) -> torch.Tensor:
+    """Embeddings as a float32 CUDA tensor.  A model that offers ``embed(batch) -> CUDA tensor`` (MobileFaceNetModel)
+    keeps them on the device: pinned host batch -> async H2D -> forward -> straight into the filter, no NumPy round
+    trip (the reference goes device -> NumPy -> Python loop per row, :184-189).  Any other model goes through
+    ``predict`` (the reference's contract)."""
+    if not hasattr(model, "embed"):
+        return torch.from_numpy(_embed_paths(model, paths, batch_size)).to(device)
+    outs = []
+    for s in range(0, len(paths), batch_size):
+        batch = torch.stack([read_and_preprocess_img(p) for p in paths[s:s + batch_size]]).pin_memory()
+        outs.append(model.embed(batch.to(device, non_blocking=True)).float())
+    return torch.cat(outs, dim=0) if outs else torch.zeros((0, 0), dtype=torch.float32, device=device)
+
+
 def get_ref_mean_vec_and_thres_from_imgs(model, ref_class_path: str,
                                          max_ref_img_count: int = 32) -> Tuple[np.ndarray, np.float32]:
     """Reference :71-100.  Embeds at most ``max_ref_img_count`` reference images one at a time (batch 1, like
@@ -161,8 +175,9 @@ def get_parsed_args(argv=None):
 
 def filter_class(model, ref_class_path: str, unfiltered_class_path: str, clean_dir: str, unclean_dir: str,
                  batch_size: int = 32, ref_img_per_class: int = 32, gallery: bool = False, threshold: float = 0.5,
-                 device: str = "cuda:0"):
-    """One iteration of the reference's per-class loop (:161-199).  Returns (similar_cnt, total, keep mask)."""
+                 device: str = "cuda:0", ref_stats=None):
+    """One iteration of the reference's per-class loop (:161-199).  Returns (similar_cnt, total, keep mask).
+    ``ref_stats`` = (mean [1, D] CUDA, thres float) when the caller computed all classes' statistics up front."""
     dev = torch.device(device)
     cls = unfiltered_class_path.split('/')[-1]
     filtered_class_clean_dir = os.path.join(clean_dir, cls)
@@ -173,8 +188,10 @@ def filter_class(model, ref_class_path: str, unfiltered_class_path: str, clean_d
     X_imgs = sorted(glob.glob(unfiltered_class_path + "/*.jpg"))
     if gallery:
         ref_imgs = sorted(glob.glob(ref_class_path + "/*.jpg"))[:ref_img_per_class]
-        ref = torch.from_numpy(_embed_paths(model, ref_imgs, batch_size)).to(dev)
+        ref = _embed_paths_device(model, ref_imgs, batch_size, dev)
         thr, metric = threshold, "cosine"
+    elif ref_stats is not None:
+        ref, thr, metric = ref_stats[0].reshape(1, -1), float(ref_stats[1]), "euclid"
     else:
         print(f"Calculating ref mean vector for {ref_class_path}")
         ref_mean_vec, thres = get_ref_mean_vec_and_thres_from_imgs(model, ref_class_path, max_ref_img_count=ref_img_per_class)
@@ -183,13 +200,35 @@ def filter_class(model, ref_class_path: str, unfiltered_class_path: str, clean_d
     total = len(X_imgs)
     if total == 0:
         return 0, 0, np.zeros(0, dtype=np.uint8)
-    cand = torch.from_numpy(_embed_paths(model, X_imgs, batch_size)).to(dev)
+    cand = _embed_paths_device(model, X_imgs, batch_size, dev)
     keep = ops.face_filter(ref, cand, thr, metric=metric).keep.cpu().numpy()      # the hot path (:186-189)
     similar_cnt = int(keep.sum())
     for path, k in zip(X_imgs, keep):
         name = path.split('/')[-1]
         shutil.copy(path, os.path.join(filtered_class_clean_dir if k else filtered_class_unclean_dir, name))
     return similar_cnt, total, keep
+
+
+def all_ref_stats(model, ref_class_paths: List[str], ref_img_per_class: int, device: str = "cuda:0"):
+    """Mean vector and threshold of EVERY class in one kernel launch (K5 batched): the reference embeds and reduces
+    one class at a time (:161-164).  Returns a list of (mean [1, D] CUDA tensor, thres float)."""
+    dev = torch.device(device)
+    feats, counts = [], []
+    for path in ref_class_paths:
+        imgs = sorted(glob.glob(path + "/*.jpg"))[:ref_img_per_class]
+        f = _embed_paths_device(model, imgs, 1, dev)                 # batch 1 like the reference (:77)
+        print(f"Calculating ref mean vector for {path}")
+        print(f"number of samples considered for reference={len(imgs)}", f"ref mean shape={(1, f.shape[1]) if len(imgs) else None}",
+              f"ref feat shape={(len(imgs), 1, f.shape[1] if len(imgs) else 0)}")
+        feats.append(f)
+        counts.append(len(imgs))
+    dim = max((f.shape[1] for f in feats if f.numel()), default=0)
+    feats = [f if f.numel() else torch.zeros((0, dim), dtype=torch.float32, device=dev) for f in feats]
+    mean, thres = ops.ref_mean_and_thres_batched(torch.cat(feats, dim=0), counts)
+    thres_h = thres.cpu().numpy()
+    for t in thres_h:
+        print("max dist from mean in the reference batch: ", t)
+    return [(mean[i:i + 1], float(thres_h[i])) for i in range(len(counts))]
 
 
 def main(argv=None, model=None):
@@ -224,10 +263,12 @@ def main(argv=None, model=None):
         it = tqdm.tqdm(ref_class_paths)
     except ImportError:
         it = ref_class_paths
+    stats = None if args.gallery else all_ref_stats(model, ref_class_paths, args.ref_img_per_class, args.device)
     for i, ref_class_path in enumerate(it):
         similar_cnt, total, _ = filter_class(model, ref_class_path, unfiltered_class_paths[i], clean_dir, unclean_dir,
                                              batch_size=args.batch_size, ref_img_per_class=args.ref_img_per_class,
-                                             gallery=args.gallery, threshold=args.threshold, device=args.device)
+                                             gallery=args.gallery, threshold=args.threshold, device=args.device,
+                                             ref_stats=None if stats is None else stats[i])
         # the reference divides unconditionally (ZeroDivisionError on an empty class, :199); keep that behaviour
         print(f"Similar images percentage={similar_cnt/total:2.2f}%, positive={similar_cnt}, total={total}")
 

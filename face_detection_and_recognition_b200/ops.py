@@ -177,6 +177,64 @@ def ref_mean_and_thres(ref_feat: torch.Tensor) -> Tuple[torch.Tensor, torch.Tens
     return mean, thres
 
 
+def ref_mean_and_thres_batched(ref_feat: torch.Tensor, counts) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All classes in one launch: ``ref_feat`` [sum(counts), D] float32 CUDA holds the reference embeddings of class 0,
+    then class 1, ...; returns (mean [C, D], thres [C]) with the per-class arithmetic of ``ref_mean_and_thres``."""
+    lib = _lib.load()
+    ref_feat = _require_cuda(ref_feat, "ref_feat")
+    dev = ref_feat.device
+    counts = [int(c) for c in counts]
+    if sum(counts) != ref_feat.shape[0]:
+        raise ValueError("counts must sum to the number of reference rows")
+    offs = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32, device=dev)
+    d = ref_feat.shape[1]
+    mean = torch.empty((len(counts), d), dtype=torch.float32, device=dev)
+    thres = torch.empty((len(counts),), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ffr_ref_mean_and_thres_batched(ref_feat.data_ptr(), offs.data_ptr(), len(counts), d, mean.data_ptr(),
+                                                 thres.data_ptr(), _stream_ptr(dev)))
+    return mean, thres
+
+
+class FaceGallery:
+    """Device-resident face gallery with the reference tracker's semantics (extract_and_label_faces_from_dataset.py
+    :101-121): ``match`` processes the queries in order; the FIRST gallery entry that satisfies
+    ``(dist < normal_thres and iou > 0.1) or dist < harsh_thres`` is overwritten by the query, otherwise the query is
+    appended.  Returns (found bool[q], faceid int[q]) with faceid = position + 1 like ``add_face`` (:118-121)."""
+
+    def __init__(self, dim: int, capacity: int = 4096, metric="cosine", normal_thres: float = 1.0,
+                 harsh_thres: float = 0.72, device: int = 0):
+        self._lib = _lib.load()
+        self.dev = torch.device("cuda", device)
+        self.dim, self.capacity, self.metric = dim, capacity, _METRICS[metric]
+        self.normal_thres, self.harsh_thres = float(normal_thres), float(harsh_thres)
+        self.feat = torch.zeros((capacity, dim), dtype=torch.float32, device=self.dev)
+        self.bbox = torch.zeros((capacity, 4), dtype=torch.float32, device=self.dev)
+        self.count = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+
+    def __len__(self) -> int:
+        return int(self.count.item())
+
+    def clear(self):
+        self.count.zero_()
+
+    def match(self, feats, bboxes=None):
+        q = torch.as_tensor(feats, dtype=torch.float32).to(self.dev).contiguous().reshape(-1, self.dim)
+        b = None if bboxes is None else torch.as_tensor(bboxes, dtype=torch.float32).to(self.dev).contiguous().reshape(-1, 4)
+        out = torch.empty((q.shape[0],), dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            check(self._lib.ffr_first_match_stream(self.feat.data_ptr(), self.bbox.data_ptr(), self.count.data_ptr(),
+                                                   self.capacity, q.data_ptr(), b.data_ptr() if b is not None else None,
+                                                   q.shape[0], self.dim, self.metric, self.normal_thres, self.harsh_thres,
+                                                   out.data_ptr(), _stream_ptr(self.dev)))
+        m = out.cpu().numpy()
+        if (m == np.iinfo(np.int32).min).any():
+            raise RuntimeError(f"gallery capacity {self.capacity} exhausted")
+        found = m >= 0
+        faceid = np.where(found, m, -1 - m) + 1
+        return found, faceid.astype(np.int32)
+
+
 class HostFilter:
     """Host-buffer entry point (ffr_ctx_*): NumPy / pinned-torch arrays in, NumPy arrays out; candidates are
     streamed to the GPU in chunks while the previous chunk is being filtered."""

@@ -111,6 +111,23 @@ int ffr_filter_stats(const void* workspace, int64_t out[4], ffr_stream_t stream)
 int ffr_ref_mean_and_thres(const float* ref_feat, int32_t n_ref, int32_t dim,
                            float* mean, float* thres, ffr_stream_t stream);
 
+/* all classes in one launch: class c owns rows offsets[c] .. offsets[c+1]-1 of ref_feat (offsets: device int32
+ * [n_classes + 1]); mean f32[n_classes, dim], thres f32[n_classes].  Same arithmetic per class as above. */
+int ffr_ref_mean_and_thres_batched(const float* ref_feat, const int32_t* offsets, int32_t n_classes, int32_t dim,
+                                   float* mean, float* thres, ffr_stream_t stream);
+
+/* ---- streaming first-match gallery scan ("next" row: the reference's face tracker) -------------------
+ * replaces Net.check_if_face_exists + add_face, face_extraction/extract_and_label_faces_from_dataset.py:101-121.
+ * Queries are processed IN ORDER against a device-resident gallery (feat f32[capacity, dim], bbox f32[capacity, 4],
+ * *gallery_count entries in use): the first entry i (ascending) with
+ *     (dist < normal_thres and iou(bbox_i, query_bbox) > 0.1) or dist < harsh_thres
+ * is overwritten by the query and match_idx[q] = i; otherwise the query is appended at position p = old count and
+ * match_idx[q] = -1 - p (INT32_MIN if the gallery is full).  dist = 1 - cos (FFR_METRIC_COSINE, :106) or the Euclid
+ * distance (FFR_METRIC_EUCLID, :104).  query_bbox may be NULL (iou = 0: only the harsh threshold can match). */
+int ffr_first_match_stream(float* gallery_feat, float* gallery_bbox, int32_t* gallery_count, int32_t capacity,
+                           const float* queries, const float* query_bbox, int32_t n_queries, int32_t dim, int metric,
+                           float normal_thres, float harsh_thres, int32_t* match_idx, ffr_stream_t stream);
+
 /* ---- host-buffer ("plugin") entry points -----------------------------------------------------
  * Same semantics as ffr_filter with HOST pointers: candidates are streamed host->device in chunks on
  * one stream while the previous chunk is filtered on another; results are copied back.  Pinned host

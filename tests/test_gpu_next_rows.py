@@ -1,0 +1,75 @@
+"""GPU tests of the "next" rows: batched reference statistics (K5 over all classes) and the streaming
+first-match gallery scan, both against outputs of the reference itself (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(ffr_lib, cuda_dev):
+    from face_detection_and_recognition_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("name", ["ref_main_facenetlike.npz", "ref_main_mobilefacenet.npz"])
+def test_batched_ref_stats_match_reference_main(ops, golden_dir, name):
+    """One launch for all classes == the (mean, thres) the reference's main() computed class by class (:85-99)."""
+    g = np.load(os.path.join(golden_dir, name))
+    feats = [g[f"c{c}_ref_feat"].reshape(-1, g[f"c{c}_ref_feat"].shape[-1]) for c in range(3)]
+    counts = [f.shape[0] for f in feats]
+    mean, thres = ops.ref_mean_and_thres_batched(torch.from_numpy(np.concatenate(feats)).cuda(), counts)
+    for c in range(3):
+        np.testing.assert_allclose(mean[c:c + 1].cpu().numpy(), g[f"c{c}_mu"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(float(thres[c]), float(g[f"c{c}_thres"]), rtol=1e-6)
+        m1, t1 = ops.ref_mean_and_thres(torch.from_numpy(feats[c]).cuda())
+        assert torch.equal(m1, mean[c:c + 1]) and float(t1) == float(thres[c])
+
+
+def test_batched_ref_stats_ragged(ops):
+    rng = np.random.default_rng(3)
+    counts = [1, 32, 7, 100]
+    x = rng.standard_normal((sum(counts), 200)).astype(np.float32) * 5
+    mean, thres = ops.ref_mean_and_thres_batched(torch.from_numpy(x).cuda(), counts)
+    o = 0
+    for c, n in enumerate(counts):
+        mu, th = oracle.ref_mean_vec_and_thres(x[o:o + n][:, None, :], n)
+        np.testing.assert_allclose(mean[c].cpu().numpy(), mu[0], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(float(thres[c]), float(th), rtol=2e-6, atol=1e-6)
+        o += n
+
+
+@pytest.mark.parametrize("tag,metric,dim", [("mfn", "euclid", 512), ("reid", "cosine", 256)])
+def test_first_match_stream_matches_reference_tracker(ops, golden_dir, tag, metric, dim):
+    """FaceGallery.match == the (found, faceid) sequence Net.check_if_face_exists / add_face produced in the
+    reference (extract_and_label_faces_from_dataset.py:101-121), for the Euclid (MobileFaceNet) and cosine branches."""
+    g = np.load(os.path.join(golden_dir, "label_scan_ref.npz"))
+    feats, bboxes = g[f"{tag}_feats"], g[f"{tag}_bboxes"]
+    want_found, want_id = g[f"{tag}_found"].astype(bool), g[f"{tag}_faceid"]
+    gal = ops.FaceGallery(dim, capacity=256, metric=metric, normal_thres=1.0, harsh_thres=0.72)
+    # all queries in one launch (sequential inside the kernel) ...
+    found, faceid = gal.match(feats, bboxes)
+    assert np.array_equal(found, want_found), np.flatnonzero(found != want_found)
+    assert np.array_equal(faceid[want_found], want_id[want_found])
+    assert len(gal) == int((~want_found).sum())
+    # ... and one query per call give the same trajectory
+    gal2 = ops.FaceGallery(dim, capacity=256, metric=metric)
+    f2 = np.array([gal2.match(feats[i], bboxes[i])[0][0] for i in range(len(feats))])
+    assert np.array_equal(f2, want_found)
+
+
+def test_first_match_capacity_and_no_bbox(ops):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((10, 64)).astype(np.float32)
+    gal = ops.FaceGallery(64, capacity=4, metric="cosine")
+    found, faceid = gal.match(x[:4])                 # four unrelated faces fill the gallery
+    assert not found.any() and list(faceid) == [1, 2, 3, 4]
+    found, faceid = gal.match(x[2] * 3.0)            # a scaled copy: cosine distance 0 < harsh threshold
+    assert found[0] and faceid[0] == 3
+    with pytest.raises(RuntimeError):
+        gal.match(x[5])
