@@ -207,12 +207,13 @@ struct KParams {
     RecheckLists lists;
     int no_recheck;
     float* dbg_scores;
+    int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
     unsigned long long* prof;      // optional [gridDim.x][16] stall-cycle counters (diagnostics)
 };
 
 // kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8|16) = 4 TMEM lane quadrants x kEW/4 column parts.
-template <int kCG, int kEW, bool kX64>
+template <int kCG, int kEW, bool kWholePart>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const KParams p) {
@@ -322,7 +323,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
                 for (int rt = 0; rt < n_rt; ++rt) {
-                    const uint32_t acc = t_it & 1, tph = (t_it >> 1) & 1;
+                    const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
+                    const uint32_t tph = p.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
                     uint32_t n_mma = kTileN;
@@ -389,7 +391,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             float gate = -INFINITY;                             // running best - delta
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
-                const uint32_t acc = t_it & 1, tph = (t_it >> 1) & 1;
+                const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
+                const uint32_t tph = p.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                 mbar_wait_timed(&t_full[acc], tph, pr, w_tfull);
                 tc_fence_after();
                 int64_t ncols64 = p.n_ref - static_cast<int64_t>(rt) * kTileN;
@@ -401,34 +404,31 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 // stream this warp's column part out of TMEM chunk by chunk: the next chunk's tcgen05.ld is in flight
                 // while the current one is reduced.  (Measured alternatives that were slower: 16 epilogue warps; loading
                 // the whole part before reducing; a reduce-only first pass that re-reads flagged chunks.)
-                if constexpr (kX64) {
-                    // 64-column tcgen05.ld variant: half as many load / wait round trips per part
-                    float wa[64], wb[64];
-                    const int g_beg = c_beg >> 1, g_end = (c_end + 1) >> 1;
-                    auto handle = [&](float (&wv)[64], int g) {
+                if constexpr (kWholePart) {
+                    // whole-part variant: pull all of this warp's columns out of TMEM back to back, hand the
+                    // accumulator stage back to the MMA warp at once, then reduce from registers
+                    float v[kChunksPerPart][32];
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            float (&v32)[32] = *reinterpret_cast<float (*)[32]>(&wv[32 * hh]);
-                            const int c = 2 * g + hh;
-                            if (c >= c_end) continue;
-                            if (ncols - c * 32 < 32) mask_chunk(v32, ncols - c * 32);
+                    for (int cc = 0; cc < kChunksPerPart; ++cc)
+                        if (c_beg + cc < c_end) tmem_ld_32x32(taddr + (c_beg + cc) * 32, v[cc]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
+                        else                     mbar_arrive(&t_empty[acc]);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < kChunksPerPart; ++cc) {
+                        const int c = c_beg + cc;
+                        if (c < c_end) {
+                            if (ncols - c * 32 < 32) mask_chunk(v[cc], ncols - c * 32);
                             if (p.dbg_scores != nullptr && row < p.n_cand) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = v32[j];
+                                    if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = v[cc][j];
                             }
-                            process_chunk(v32, col0 + c * 32, p.delta, t, gate);
-                        }
-                    };
-                    if (g_beg < g_end) tmem_ld_32x64(taddr + g_beg * 64, wa);
-                    for (int g = g_beg; g < g_end; g += 2) {
-                        tmem_ld_wait();
-                        if (g + 1 < g_end) tmem_ld_32x64(taddr + (g + 1) * 64, wb);
-                        handle(wa, g);
-                        if (g + 1 < g_end) {
-                            tmem_ld_wait();
-                            if (g + 2 < g_end) tmem_ld_32x64(taddr + (g + 2) * 64, wa);
-                            handle(wb, g + 1);
+                            process_chunk(v[cc], col0 + c * 32, p.delta, t, gate);
                         }
                     }
                 } else {
@@ -460,11 +460,13 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     }
                 }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
-                    else                     mbar_arrive(&t_empty[acc]);
+                if constexpr (!kWholePart) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
+                        else                     mbar_arrive(&t_empty[acc]);
+                    }
                 }
                 ++t_it;
             }
@@ -649,11 +651,14 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
     p.thr = thr; p.delta = delta; p.thr_band = thr_band; p.ref_index_base = ref_index_base;
     p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
+    p.acc_stages = env_int("FFR_ACC_STAGES", 2) == 1 ? 1 : 2;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-    const bool x64 = env_int("FFR_EPI_X64", 0) != 0;
-    KernelFn fn = cg == 1 ? (x64 ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)
-                          : (x64 ? filter_mma_kernel<2, 8, true> : filter_mma_kernel<2, 8, false>);
+    // whole-part epilogue (TMEM stage handed back before the max tree) measured 3-6 % faster for dim >= 256, slower for
+    // short tiles (dim 128, few reference tiles)
+    const bool wp = env_int("FFR_EPI_WHOLE", dim_pad >= 256 ? 1 : 0) != 0;
+    KernelFn fn = cg == 1 ? (wp ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)
+                          : (wp ? filter_mma_kernel<2, 8, true> : filter_mma_kernel<2, 8, false>);
     static bool attr_set = false;
     if (!attr_set) {
         FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
