@@ -34,6 +34,10 @@ WORKLOADS = {
                  name="configs[3] per-GPU shard: 10k ref x 1.25M cand x 512-d (10M candidates over 8 GPUs)"),
     "cfg4": dict(n_ref=100_000, n_cand=1_250_000, dim=128,
                  name="configs[4] per-GPU shard: 100k ref x 1.25M cand x 128-d (10M candidates over 8 GPUs)"),
+    # the reference's literal mode (filter_faces_using_reference.py:186-189) at scale: ONE mean vector, Euclid keep test.
+    # 0.5 FLOP/byte: the HBM-bound end of the path (exact fp32 streaming kernel K2s, no tensor cores)
+    "n1": dict(n_ref=1, n_cand=10_000_000, dim=128, metric="euclid", thr=1.2,
+               name="reference literal mode: 1 mean vector x 10M cand x 128-d, Euclid keep test (HBM-bound)"),
 }
 THR = 0.5
 BLOCK = 62_500            # rows per synthetic block; data of a global row never depends on the GPU count
@@ -125,7 +129,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_port_rate(n_ref, dim, n_sample, seconds_target=None, threads=None):
+def cpu_port_rate(n_ref, dim, n_sample, seconds_target=None, threads=None, metric="cosine", thr=THR):
     """Times the oracle (the CPU restatement of the reference's arithmetic) on a bounded candidate-axis sample of the
     workload: vectorised fp32 normalise + R @ C^T + max/argmax + threshold, all host threads, NumPy and torch-CPU
     (the faster one is reported), plus the reference's literal per-pair Python loop on a tiny sub-sample."""
@@ -137,6 +141,20 @@ def cpu_port_rate(n_ref, dim, n_sample, seconds_target=None, threads=None):
     torch.set_num_threads(threads)
     rng = np.random.default_rng(42)
     ref = rng.standard_normal((n_ref, dim), dtype=np.float32)
+    if metric == "euclid":
+        # filter_faces_using_reference.py:186-189: vectorised (diff, row norm, <=) on all threads and the literal loop
+        n_sample = int(min(n_sample, 4_000_000))
+        cand = rng.standard_normal((n_sample, dim), dtype=np.float32)
+        tc = torch.from_numpy(cand); tr = torch.from_numpy(ref)
+        t = time.perf_counter(); k = (torch.linalg.vector_norm(tc - tr, dim=1) <= thr); t_torch = time.perf_counter() - t
+        t = time.perf_counter(); k = (torch.linalg.vector_norm(tc - tr, dim=1) <= thr); t_torch = min(t_torch, time.perf_counter() - t)
+        n_np = n_sample // 4
+        t = time.perf_counter(); kn = oracle.filter_euclid(ref, cand[:n_np], thr)[0]; t_np = time.perf_counter() - t
+        assert (k[:n_np].numpy().astype(np.uint8) == kn).mean() > 0.9999
+        t = time.perf_counter(); oracle.euclid_keep_literal(cand[:100_000], ref, thr); r_lit = 100_000 / (time.perf_counter() - t)
+        r_torch, r_np = n_ref * n_sample / t_torch, n_ref * n_np / t_np
+        return dict(value=max(r_torch, r_np), torch_cpu=r_torch, numpy=r_np, literal_loop=r_lit, threads=threads,
+                    n_sample=n_sample, seconds=t_torch)
     probe = rng.standard_normal((min(2048, n_sample), dim), dtype=np.float32)
     t = time.perf_counter(); oracle.filter_cosine_torch(ref, probe, THR); t_probe = time.perf_counter() - t
     t = time.perf_counter(); oracle.filter_cosine_torch(ref, probe, THR); t_probe = min(t_probe, time.perf_counter() - t)
@@ -167,32 +185,41 @@ def run_reference(args, rank, world, emit):
     import torch
     w = WORKLOADS[args.workload]
     n_ref, dim = w["n_ref"], w["dim"]
-    probe = cpu_port_rate(n_ref, dim, 4096)                        # sizes the per-step sample for ~1.5 s
-    n_sample = int(max(2048, min(w["n_cand"], 1.5 * probe["value"] / n_ref)))
+    metric, thr = w.get("metric", "cosine"), w.get("thr", THR)
     import numpy as np
     from oracle import oracle
+    probe = cpu_port_rate(n_ref, dim, 4096 if metric == "cosine" else 400_000, metric=metric, thr=thr)
+    n_sample = int(max(2048, min(w["n_cand"], 1.5 * probe["value"] / n_ref)))       # ~1.5 s per step
     rng = np.random.default_rng(42)
     ref = rng.standard_normal((n_ref, dim), dtype=np.float32)
     cand = rng.standard_normal((n_sample, dim), dtype=np.float32)
-    fn = oracle.filter_cosine_torch if probe["torch_cpu"] >= probe["numpy"] else oracle.filter_cosine
+    if metric == "euclid":
+        tr, tc = torch.from_numpy(ref), torch.from_numpy(cand)
+        use_torch = probe["torch_cpu"] >= probe["numpy"]
+        fn = (lambda r, c, t: (torch.linalg.vector_norm(tc - tr, dim=1) <= t)) if use_torch else oracle.filter_euclid
+        how = ("torch-CPU" if use_torch else "NumPy") + " (diff, row norm, <=)"
+    else:
+        use_torch = probe["torch_cpu"] >= probe["numpy"]
+        fn = oracle.filter_cosine_torch if use_torch else oracle.filter_cosine
+        how = ("torch-CPU" if use_torch else "NumPy") + " sgemm + max/argmax + threshold"
     for _ in range(args.warmup):
-        fn(ref, cand, THR)
+        fn(ref, cand, thr)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fn(ref, cand, THR)
+        fn(ref, cand, thr)
     dt = time.perf_counter() - t0
     value = n_ref * n_sample * args.steps / dt
     cores = torch.get_num_threads()
     sample = (f"{n_sample} of {w['n_cand']} candidates per step x all {n_ref} references x {dim}-d, vectorised fp32 "
-              f"restatement ({'torch-CPU' if fn is oracle.filter_cosine_torch else 'NumPy'} sgemm + max/argmax + threshold), "
-              f"{cores} threads; literal per-pair Python loop = {probe['literal_loop']:.3g} pairs/s on 1 thread")
+              f"restatement ({how}), {cores} threads; the reference's literal per-row Python loop = "
+              f"{probe['literal_loop']:.3g} pairs/s on 1 thread")
     emit({
         "impl": "reference", "metric": "face pairs compared/sec (ref x cand cosine+filter)", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "n_ref": n_ref, "n_cand_per_gpu": w["n_cand"], "dim": dim, "threshold": THR,
-                   "metric": "cosine"},
+        "config": {"workload": w["name"], "n_ref": n_ref, "n_cand_per_gpu": w["n_cand"], "dim": dim, "threshold": thr,
+                   "metric": metric},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -240,6 +267,7 @@ def main():
     lib = _lib.load()
     w = WORKLOADS[args.workload]
     n_ref, n_cand, dim = w["n_ref"], w["n_cand"], w["dim"]
+    metric, thr = w.get("metric", "cosine"), w.get("thr", THR)
     pk = peaks()
 
     ref = make_refs(n_ref, dim, dev)
@@ -252,7 +280,7 @@ def main():
     gather = ops.ResultGather(rank, world, local_rank) if world > 1 else None
 
     def step(i):
-        r = ops.face_filter(ref, cands[i % n_buf], THR, out=(keep, idx, val))
+        r = ops.face_filter(ref, cands[i % n_buf], thr, metric=metric, out=(keep, idx, val))
         if gather is not None:
             return gather.all_gather(r.keep, r.best_idx)
         return r.keep, r.best_idx
@@ -284,8 +312,9 @@ def main():
     t_host1 = time.perf_counter()
     launches = ops.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
-    k2_ms = statistics.mean(a.elapsed_time(b) for a, b in k2_ev)
-    stats = ops.face_filter(ref, cands[0], THR, out=(keep, idx, val), want_stats=True).stats
+    tensor_path = metric == "cosine" and n_ref > 8
+    k2_ms = statistics.mean(a.elapsed_time(b) for a, b in k2_ev) if tensor_path else ms_total / args.steps
+    stats = ops.face_filter(ref, cands[0], thr, metric=metric, out=(keep, idx, val), want_stats=True).stats
     keep_frac = float(keep.float().mean())
     clocks = sampler.stop(t_host0, t_host1) if sampler else None
 
@@ -298,12 +327,12 @@ def main():
         out_h = (torch.empty(n_cand, dtype=torch.uint8).pin_memory(), torch.empty(n_cand, dtype=torch.int32).pin_memory(),
                  torch.empty(n_cand, dtype=torch.float32).pin_memory())
         hf = ops.HostFilter(device=local_rank, max_ref=n_ref, chunk_cand=min(n_cand, 1 << 17), max_dim=dim)
-        hf(ref_h, cand_h, THR, out=out_h)
+        hf(ref_h, cand_h, thr, metric=metric, out=out_h)
         e2e_steps = max(2, min(args.steps, 10))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            hf(ref_h, cand_h, THR, out=out_h)
+            hf(ref_h, cand_h, thr, metric=metric, out=out_h)
         t_e2e = time.perf_counter() - t0
         same = bool(torch.equal(out_h[0], keep.cpu()) and torch.equal(out_h[1], idx.cpu()))
         hf.close()
@@ -334,9 +363,12 @@ def main():
             "metric": "face pairs compared/sec (ref x cand cosine+filter)",
             "value": pairs_job / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (tcgen05 kind::f16); f32 re-check", "data": "synthetic",
-            "config": {"workload": w["name"], "n_ref": n_ref, "n_cand_per_gpu": n_cand, "dim": dim, "threshold": THR,
-                       "metric": "cosine", "sharding": "candidate axis; references replicated; one NCCL allgather of 5 B/candidate"
+            "vs_baseline": None, "dtype": "f16->f32" if tensor_path else "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "n_ref": n_ref, "n_cand_per_gpu": n_cand, "dim": dim, "threshold": thr,
+                       "metric": metric,
+                       "arithmetic": ("tcgen05 kind::f16: fp16 operands, fp32 accumulate in TMEM; fp32 re-check of near-tie / "
+                                      "near-threshold rows") if tensor_path else "fp32 CUDA cores (exact streaming kernel)",
+                       "sharding": "candidate axis; references replicated; one NCCL allgather of 5 B/candidate"
                        if world > 1 else "single GPU",
                        "l2": (f"inputs {in_bytes / 1e6:.0f} MB per GPU > L2 (126 MB)" if n_buf == 1 else
                               f"rotating {n_buf} input copies ({n_buf * in_bytes / 1e6:.0f} MB > L2 126 MB)"),
@@ -350,6 +382,11 @@ def main():
                                       "frac_of_hbm_peak": hbm_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm"]}},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if not tensor_path:            # one HBM-bound kernel: the roofline is the measured copy bandwidth
+            gbs = hbm_bytes / (ms_step * 1e-3) / 1e9
+            out["roofline"] = {"bound": "hbm", "kernel": "filter_fp32_kernel (K2s)", "achieved": gbs, "peak": pk["hbm"],
+                               "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["source"],
+                               "bytes_per_launch": hbm_bytes, "traffic": traffic}
         if e2e:
             out["e2e"] = {"value": pairs_job / e2e["seconds"], "unit": "pairs/s",
                           "h2d_bytes_per_step": int((n_cand + n_ref) * dim * 4), "d2h_bytes_per_step": int(9 * n_cand),
@@ -357,7 +394,7 @@ def main():
                           "api": "ffr_ctx_filter_host (pinned host buffers, chunked H2D overlapped with compute)",
                           "same_result_as_device_path": e2e["same_as_device_path"]}
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_port_rate(n_ref, dim, n_cand, seconds_target=10.0)
+            cb = cpu_port_rate(n_ref, dim, n_cand, seconds_target=10.0, metric=metric, thr=thr)
             out["cpu_baseline"] = {
                 "value": cb["value"], "unit": "pairs/s", "cores": cb["threads"], "kind": "port",
                 "sample": (f"{cb['n_sample']} of {n_cand} candidates x all {n_ref} references x {dim}-d "

@@ -136,6 +136,7 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     const int32_t ld = ffr_padded_dim(dim);
     const __half* ref16 = ref16_pre;
     const __half* cand16 = nullptr;
+    const float* fuse_cand = nullptr;        // non-null: K2 normalises the candidates itself (K1 fused)
     int launches = 0;
     int rc;
     if (dtype == FFR_DTYPE_F32) {
@@ -146,11 +147,14 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
             ref16 = r16;
             ++launches;
         }
-        __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
-        rc = launch_l2norm(static_cast<const float*>(cand), n_cand, dim, c16, ld, nullptr, nullptr, s);
-        if (rc != FFR_OK) return rc;
-        cand16 = c16;
-        ++launches;
+        fuse_cand = filter_mma_can_fuse(static_cast<const float*>(cand), dim, ld) ? static_cast<const float*>(cand) : nullptr;
+        if (fuse_cand == nullptr) {
+            __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
+            rc = launch_l2norm(static_cast<const float*>(cand), n_cand, dim, c16, ld, nullptr, nullptr, s);
+            if (rc != FFR_OK) return rc;
+            cand16 = c16;
+            ++launches;
+        }
     } else {
         if (ref16 == nullptr) ref16 = static_cast<const __half*>(ref);
         cand16 = static_cast<const __half*>(cand);
@@ -169,7 +173,7 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     float thr_band = delta;
     if (band_count != nullptr && band_tol + delta > thr_band) thr_band = band_tol + delta;
     if (g_ev_k2_begin != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_begin, s));
-    rc = launch_filter_mma(ref16, n_ref, cand16, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
+    rc = launch_filter_mma(ref16, n_ref, cand16, fuse_cand, dim, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
                            best_val, lists, recheck ? 0 : 1, s);
     if (rc != FFR_OK) return rc;
     if (g_ev_k2_end != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_end, s));

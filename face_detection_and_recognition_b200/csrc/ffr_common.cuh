@@ -224,7 +224,9 @@ int launch_l2norm(const float* x, int64_t rows, int32_t dim, __half* y16, int32_
 int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim, int metric,
                        float thr, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                        float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
-int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
+bool filter_mma_can_fuse(const float* cand32, int32_t dim, int32_t dim_pad);
+int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, const float* cand32, int32_t dim,
+                      int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, cudaStream_t s);
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,

@@ -222,6 +222,16 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
         assert res.stats["rechecked"] >= 900
 
 
+@pytest.mark.parametrize("n_ref,n_cand,dim", [(300, 5000, 128), (1000, 3001, 256), (64, 700, 64), (500, 129, 192)])
+def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
+    """Experimental K2 variant that normalises the fp32 candidates in-kernel (FFR_FUSE_K1=1, off by default because it
+    is slower): same parity bar as the default K1 + K2 path."""
+    monkeypatch.setenv("FFR_FUSE_K1", "1")
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + n_ref, n_adversarial=100, n_dup_refs=8, unit_norm=False)
+    res = _check_cosine(ops, ref, cand, 0.5)
+    assert res.stats["launches"] == 4                      # K1(ref) + K2 + K3a + K3b: no K1 over the candidates
+
+
 def test_filter_mma_config2_full(ops):
     """BASELINE configs[1] in full: 1k references x 100k candidates x 128-d, threshold 0.5."""
     ref, cand = oracle.make_synthetic(1000, 100_000, 128, seed=42, n_adversarial=1000, n_dup_refs=100)

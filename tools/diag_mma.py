@@ -97,6 +97,9 @@ def prof(n_ref, n_cand, dim):
           f"t_empty {ml[6] / ml[4]:.1%}, b_full {ml[7] / ml[4]:.1%}")
     print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
           f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
+    if m[12] > 0:
+        print(f"    converter 0: total {m[12]:.3e} cyc; waiting a_empty {m[13] / m[12]:.1%}; busy {(m[12] - m[13]) / max(m[14], 1):.0f} cyc "
+              f"per candidate tile ({m[14]:.0f} tiles)", flush=True)
 
 
 if __name__ == "__main__":
@@ -123,6 +126,7 @@ if __name__ == "__main__":
         prof(10_000, 500_000, 256)
         prof(100_000, 300_000, 128)
         prof(1000, 100_000, 128)
+        prof(256, 2_000_000, 128)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
