@@ -157,6 +157,41 @@ def face_filter(ref: torch.Tensor, cand: torch.Tensor, thr: float, metric="cosin
     return res
 
 
+class GraphedFilter:
+    """``face_filter`` for fixed shapes captured once into a CUDA graph: the whole K1 -> K2 -> K3 launch sequence
+    (two memsets + five kernels) replays as ONE graph launch.  Worth it when the step is launch-bound (BASELINE
+    configs[1]: ~100 us of GPU work).  Inputs are copied into / results read from the static tensors ``ref``, ``cand``,
+    ``result``."""
+
+    def __init__(self, n_ref: int, n_cand: int, dim: int, thr: float, metric="cosine", device: int = 0, flags: int = 0):
+        self.dev = torch.device("cuda", device)
+        self.ref = torch.zeros((n_ref, dim), dtype=torch.float32, device=self.dev)
+        self.cand = torch.zeros((n_cand, dim), dtype=torch.float32, device=self.dev)
+        self.thr, self.metric, self.flags = float(thr), metric, flags
+        out = (torch.empty(n_cand, dtype=torch.uint8, device=self.dev), torch.empty(n_cand, dtype=torch.int32, device=self.dev),
+               torch.empty(n_cand, dtype=torch.float32, device=self.dev))
+        self.ref.normal_()
+        self.cand.normal_()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):                              # warm-up on the side stream (workspace, attributes)
+            face_filter(self.ref, self.cand, self.thr, metric=metric, flags=flags, out=out)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.result = face_filter(self.ref, self.cand, self.thr, metric=metric, flags=flags, out=out)
+
+    def replay(self) -> FilterResult:
+        self.graph.replay()
+        return self.result
+
+    def __call__(self, ref: torch.Tensor, cand: torch.Tensor) -> FilterResult:
+        self.ref.copy_(ref, non_blocking=True)
+        self.cand.copy_(cand, non_blocking=True)
+        return self.replay()
+
+
 def cosine_filter(ref, cand, thr, **kw) -> FilterResult:
     return face_filter(ref, cand, thr, metric="cosine", **kw)
 

@@ -133,3 +133,35 @@ def test_class_mismatch_raises(tmp_path):
     (tmp_path / "u" / "c").mkdir()
     with pytest.raises(Exception, match="did not match"):
         main(["--ud", str(tmp_path / "u"), "--rd", str(tmp_path / "r"), "--td", str(tmp_path / "t")], model=object())
+
+
+REFERENCE_MFN = "/root/reference/face_detection_and_extraction/modules/mobile_facenet"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_MFN), reason="reference checkout not mounted (authoring container only)")
+def test_mobilefacenet_adapter_wraps_the_reference_model(tmp_path):
+    """north_star: embedding extraction stays in the reference's own PyTorch MobileFaceNet.  The adapter imports that
+    class (never a copy), honours the predict() contract of filter_faces_using_reference.py:84,184 and returns exactly
+    what the reference network computes."""
+    import sys
+    import torch
+    from face_detection_and_recognition_b200.filter_faces_using_reference import MobileFaceNetModel
+    with pytest.raises(FileNotFoundError):
+        MobileFaceNetModel(str(tmp_path / "missing.pth"), REFERENCE_MFN, device="cpu")
+    torch.manual_seed(0)
+    model = MobileFaceNetModel(str(tmp_path / "missing.pth"), REFERENCE_MFN, device="cpu", allow_random_init=True)
+    assert type(model.net).__module__ == "mobile_facenet" and type(model.net).__name__ == "MobileFaceNet"
+    assert "face_detection_and_recognition_b200" not in sys.modules["mobile_facenet"].__file__
+    batch = np.random.default_rng(0).standard_normal((3, 160, 160, 3)).astype(np.float32)
+    out = model.predict(batch, verbose=0)
+    assert out.shape == (3, 512) and out.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)       # the net ends in l2_norm (:30-33,154)
+    x = torch.nn.functional.interpolate(torch.from_numpy(batch).permute(0, 3, 1, 2), size=(112, 112), mode="bilinear",
+                                        align_corners=False)
+    with torch.no_grad():
+        want = model.net(x).numpy()
+    np.testing.assert_allclose(out, want, atol=1e-6)
+    # a state dict saved from the reference class loads through -m
+    torch.save(model.net.state_dict(), str(tmp_path / "w.pth"))
+    m2 = MobileFaceNetModel(str(tmp_path / "w.pth"), REFERENCE_MFN, device="cpu")
+    np.testing.assert_allclose(m2.predict(batch), out, atol=1e-6)

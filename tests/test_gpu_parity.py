@@ -185,7 +185,8 @@ def test_mma_raw_scores(ffr_lib, ops, n_ref, n_cand, dim):
 # ---------------------------------------------------------------- K1+K2+K3 end to end
 @pytest.mark.parametrize("n_ref,n_cand,dim", [
     (9, 100, 128), (255, 1000, 128), (256, 1000, 128), (257, 1000, 128), (1000, 5000, 128), (300, 129, 512),
-    (2000, 3000, 512), (513, 1, 256), (64, 4000, 64), (700, 900, 200), (1111, 2049, 384)])
+    (2000, 3000, 512), (513, 1, 256), (64, 4000, 64), (700, 900, 200), (1111, 2049, 384), (300, 500, 50), (100, 257, 3),
+    (40, 1000, 510)])
 def test_filter_mma_vs_oracle(ops, n_ref, n_cand, dim):
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref * 7 + dim, n_adversarial=min(200, n_cand // 4),
                                       n_dup_refs=min(32, n_ref // 4))
