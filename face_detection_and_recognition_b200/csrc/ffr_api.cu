@@ -119,7 +119,9 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     WsHeader* hdr = reinterpret_cast<WsHeader*>(ws + L.hdr);
     g_last = {workspace, mma ? 1 : 0, 0};
     if (band_count != nullptr) FFR_CUDA_TRY(cudaMemsetAsync(band_count, 0, sizeof(int32_t), s));
-    FFR_CUDA_TRY(cudaMemsetAsync(hdr, 0, sizeof(WsHeader), s));
+    // the re-check header (list counters) must be zero before K2: the K1 launch does it when there is one
+    const bool k1_runs = mma && dtype == FFR_DTYPE_F32 && n_cand > 0;
+    if (!k1_runs) FFR_CUDA_TRY(cudaMemsetAsync(hdr, 0, sizeof(WsHeader), s));
     if (n_cand == 0) return FFR_OK;
 
     if (!mma) {
@@ -140,27 +142,24 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     int launches = 0;
     int rc;
     if (dtype == FFR_DTYPE_F32) {
-        if (ref16 == nullptr) {
-            __half* r16 = reinterpret_cast<__half*>(ws + L.ref16);
-            rc = launch_l2norm(static_cast<const float*>(ref), n_ref, dim, r16, ld, nullptr, nullptr, s);
-            if (rc != FFR_OK) return rc;
-            ref16 = r16;
-            ++launches;
-        }
+        // K1: references (unless the caller cached them) and candidates in ONE launch, which also zeroes the header
+        static_assert(sizeof(WsHeader) % 4 == 0 && sizeof(WsHeader) / 4 <= 256, "header is zeroed by one CTA");
+        __half* r16 = ref16 == nullptr ? reinterpret_cast<__half*>(ws + L.ref16) : nullptr;
         fuse_cand = filter_mma_can_fuse(static_cast<const float*>(cand), dim, ld) ? static_cast<const float*>(cand) : nullptr;
-        if (fuse_cand == nullptr) {
-            __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
-            rc = launch_l2norm(static_cast<const float*>(cand), n_cand, dim, c16, ld, nullptr, nullptr, s);
-            if (rc != FFR_OK) return rc;
-            cand16 = c16;
-            ++launches;
-        }
+        __half* c16 = fuse_cand == nullptr ? reinterpret_cast<__half*>(ws + L.cand16) : nullptr;
+        rc = launch_l2norm_pair(c16 ? static_cast<const float*>(cand) : nullptr, c16 ? n_cand : 0, c16,
+                                r16 ? static_cast<const float*>(ref) : nullptr, r16 ? n_ref : 0, r16, dim, ld, hdr,
+                                static_cast<int32_t>(sizeof(WsHeader) / 4), s);
+        if (rc != FFR_OK) return rc;
+        ++launches;
+        if (r16 != nullptr) ref16 = r16;
+        cand16 = c16;
     } else {
         if (ref16 == nullptr) ref16 = static_cast<const __half*>(ref);
         cand16 = static_cast<const __half*>(cand);
     }
     const bool recheck = (dtype == FFR_DTYPE_F32) && !(flags & FFR_FLAG_NO_RECHECK);
-    g_last.launches = launches + 1 + (recheck ? 2 : 0);
+    g_last.launches = launches + 1 + (recheck ? 1 : 0);
     RecheckLists lists;
     lists.hdr = hdr;
     lists.recs = reinterpret_cast<RecheckRec*>(ws + L.recs);

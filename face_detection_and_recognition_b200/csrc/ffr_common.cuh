@@ -180,6 +180,16 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float (&v)[64]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are defined only after tcgen05.wait::ld.  The compiler does not
+// know that (consumers only depend on the ld statement) and is free to hoist arithmetic on v above the wait; this empty
+// statement, placed after tmem_ld_wait(), redefines v so every use stays below it.  No instruction is emitted.
+__device__ __forceinline__ void tmem_ld_fence(float (&v)[32]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
@@ -224,6 +234,8 @@ int launch_l2norm(const float* x, int64_t rows, int32_t dim, __half* y16, int32_
 int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim, int metric,
                        float thr, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                        float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
+int launch_l2norm_pair(const float* x_a, int64_t rows_a, __half* y16_a, const float* x_b, int64_t rows_b, __half* y16_b,
+                       int32_t dim, int32_t ld16, void* zero_ptr, int32_t zero_words, cudaStream_t s);
 bool filter_mma_can_fuse(const float* cand32, int32_t dim, int32_t dim_pad);
 int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, const float* cand32, int32_t dim,
                       int64_t n_cand, int32_t dim_pad,

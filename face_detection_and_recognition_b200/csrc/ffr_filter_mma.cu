@@ -50,7 +50,7 @@ constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-bl
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;                       // 227 KiB opt-in maximum
 constexpr uint32_t kBarrierBytes = 512;                       // mbarriers + TMEM slot
-constexpr uint32_t kMergeBytes = kTileM * 7 * 4;              // top-4 hand-over of the upper column half
+constexpr uint32_t kMergeBytes = kTileM * 8 * 4;              // top-4 + amb hand-over of the upper column half
 // per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
 // running top-4 scores of one candidate (first three with their reference index): what K3 needs to decide in fp32
@@ -85,39 +85,38 @@ __device__ __forceinline__ void top3_merge_insert(Top3& t, float v, int32_t idx)
     t.b1 = g1 ? v : t.b1;
 }
 
-// v: 32 consecutive scores of this thread's candidate; base = reference index of v[0].
-// gate = running best - delta (maintained here): a chunk / 8-column group whose maximum stays below the gate cannot
-// change the top-3 window and is skipped.  The skip is a plain per-thread branch: when no lane of the warp takes it
-// the warp falls through at the cost of one compare (no vote), and ptxas reconverges the warp at the end of the
-// block, before the next warp-wide tcgen05.ld.
-__device__ __forceinline__ void process_chunk(const float (&v)[32], int32_t base, float delta, Top3& t, float& gate) {
-    float s[4];
+// Update path of the epilogue.  v: 32 consecutive scores of this thread's candidate, cmax their maximum, base = reference
+// index of v[0]; called only when cmax reaches gate = running best - delta.  After this chunk the window is
+// [max(best, cmax) - delta, ...]; the chunk maximum is inserted at its first column (ascending columns + strict '>' in
+// top3_insert = np.argmax first occurrence).  Nearly always it is the only column of the chunk inside the window; when
+// it is not, the other columns are NOT inserted: the row remembers the largest such chunk maximum in `amb`, and if
+// that is still inside the window of the final best (amb >= best - delta) the row goes to the full fp32 rescan (K3b),
+// which sees every reference.  Hidden columns are <= their chunk maximum, so amb < best - delta proves they are
+// irrelevant.  This keeps the path to ~110 instructions; the ordered insertion of every in-window column it
+// replaces was ~600 and made the whole loop body too large for the instruction cache to stream.
+__device__ __forceinline__ void update_chunk(const float (&v)[32], float cmax, int32_t base, float delta, Top3& t,
+                                             float& gate, float& amb) {
+    const float w = fmaxf(t.b1, cmax) - delta;
+    uint32_t g[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        s[k] = fmax3(fmax3(v[8 * k + 0], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
-                     fmaxf(v[8 * k + 6], v[8 * k + 7]));
-    const float cmax = fmax3(s[0], s[1], fmaxf(s[2], s[3]));
-    if (cmax >= gate) {
-        // After this chunk the window is [max(best, cmax) - delta, ...]; only columns inside it matter.  Nearly
-        // always that is the chunk maximum alone: one insertion, its column found from a 32-bit compare mask.
-        // (Measured alternatives that were slower: warp votes instead of the per-thread branch; per-8-column masks.)
-        const float w = fmaxf(t.b1, cmax) - delta;
-        uint32_t ge = 0;
+    for (int k = 0; k < 4; ++k) {                      // independent chains (FSETP + SEL + 3-input add): 2.5 ops per column
+        g[k] = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ge |= (v[j] >= w) ? (1u << j) : 0u;
-        if ((ge & (ge - 1)) == 0) {
-            top3_insert(t, cmax, base + __ffs(ge) - 1);
-        } else {                                  // several columns inside the window: ordered insertion, 8 at a time
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (s[k] >= w) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) top3_insert(t, v[8 * k + j], base + 8 * k + j);
-                }
-            }
-        }
-        gate = t.b1 - delta;
+        for (int j = 0; j < 8; ++j) g[k] |= (v[8 * k + j] >= w) ? (1u << (8 * k + j)) : 0u;
     }
+    uint32_t ge = (g[0] | g[1]) | (g[2] | g[3]);
+    if (ge & (ge - 1)) {                               // several columns inside the window (rare)
+        amb = fmaxf(amb, cmax);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g[k] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k] |= (v[8 * k + j] == cmax) ? (1u << (8 * k + j)) : 0u;
+        }
+        ge = (g[0] | g[1]) | (g[2] | g[3]);
+    }
+    if (ge != 0) top3_insert(t, cmax, base + __ffs(ge) - 1);      // (ge == 0 only with NaN scores: zero-norm rows)
+    gate = t.b1 - delta;
 }
 
 __device__ __forceinline__ float chunk_max(const float (&v)[32]) {
@@ -149,6 +148,16 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // arri
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+// Same, without release semantics: for "this warp has finished READING the accumulator stage" (t_empty).  The reads
+// are complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; no generic-proxy writes need to
+// become visible.  The .release.cluster form compiles to MEMBAR.ALL.GPU + arrive, ~1 us per reference tile.
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1,
@@ -218,8 +227,8 @@ struct KParams {
 // kFuse: the A (candidate) tile is produced in-kernel from the fp32 rows by four extra "converter" warps (row L2
 // normalisation + fp16 cast + 128-byte-swizzled store) instead of TMA-loading K1's fp16 copy: candidates are read
 // from HBM once, as fp32, and never written back.  Used when the A ring has >= 2 stages (dim <= 256).
-template <int kCG, int kEW, bool kWholePart, bool kFuse>
-__global__ void __launch_bounds__(64 + 32 * kEW + (kFuse ? 128 : 0), 1)
+template <int kCG, int kEW, bool kFuse>
+__global__ void __launch_bounds__(64 + 32 * kEW + (kFuse ? 128 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const KParams p) {
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
@@ -476,7 +485,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         uint32_t t_it = 0;
         bool first_tile = true;
         const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
-        unsigned long long w_tfull = 0;
+        unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0;
+        // diagnostics (score dump, epilogue modes) only exist in the general loop
+        const bool hot_ok = !kFuse && p.dbg_scores == nullptr && p.epi_mode == 0;
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -484,90 +495,87 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             t.i1 = 0;
             t.i2 = t.i3 = -1;
             float gate = -INFINITY;                             // running best - delta
+            float amb = -INFINITY;                              // see update_chunk
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
                 const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
                 const uint32_t tph = p.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                 mbar_wait_timed(&t_full[acc], tph, pr, w_tfull);
+                const long long tp0 = pr ? clock64() : 0;
                 tc_fence_after();
-                int64_t ncols64 = p.n_ref - static_cast<int64_t>(rt) * kTileN;
-                const int ncols = ncols64 > kTileN ? kTileN : static_cast<int>(ncols64);
-                const int c_beg = kChunksPerPart * h;
-                const int c_end = min((ncols + 31) >> 5, c_beg + kChunksPerPart);   // this warp's chunks: [c_beg, c_end)
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN;
                 const int32_t col0 = rt * kTileN;
-                // stream this warp's column part out of TMEM chunk by chunk: the next chunk's tcgen05.ld is in flight
-                // while the current one is reduced.  (Measured alternatives that were slower: 16 epilogue warps; loading
-                // the whole part before reducing; a reduce-only first pass that re-reads flagged chunks.)
-                if constexpr (kWholePart) {
-                    // whole-part variant: pull all of this warp's columns out of TMEM back to back, hand the
-                    // accumulator stage back to the MMA warp at once, then reduce from registers
+                const int64_t ncols64 = p.n_ref - static_cast<int64_t>(col0);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + h * (kChunksPerPart * 32);
+                const int32_t base0 = col0 + h * (kChunksPerPart * 32);
+                if (hot_ok) {
+                    // ---- hot loop: straight-line code.  All of this warp's columns are
+                    // pulled out of TMEM back to back, the accumulator stage goes back to the MMA warp at once, then
+                    // one max tree per 32-column chunk and ONE branch per tile guards the update path.  A taken branch
+                    // costs ~30 cycles here (two warps per scheduler cannot hide the refetch): the loop shape, not the
+                    // arithmetic, was what bounded the epilogue before (tools/epi_bench.cu).
                     float v[kChunksPerPart][32];
 #pragma unroll
-                    for (int cc = 0; cc < kChunksPerPart; ++cc)
-                        if (c_beg + cc < c_end) tmem_ld_32x32(taddr + (c_beg + cc) * 32, v[cc]);
+                    for (int cc = 0; cc < kChunksPerPart; ++cc) tmem_ld_32x32(taddr + cc * 32, v[cc]);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int cc = 0; cc < kChunksPerPart; ++cc) tmem_ld_fence(v[cc]);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
+                        if (kCG == 2 && !leader) mbar_arrive_leader_relaxed(&t_empty[acc]);
                         else                     mbar_arrive(&t_empty[acc]);
                     }
+                    if (ncols64 < kTileN) {                        // partial last reference tile: columns >= n_ref -> -inf
+                        const int n_left = static_cast<int>(ncols64) - h * (kChunksPerPart * 32);
 #pragma unroll
-                    for (int cc = 0; cc < kChunksPerPart; ++cc) {
-                        const int c = c_beg + cc;
-                        if (c < c_end) {
-                            if (ncols - c * 32 < 32) mask_chunk(v[cc], ncols - c * 32);
-                            if (p.dbg_scores != nullptr && row < p.n_cand) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = v[cc][j];
-                            }
-                            process_chunk(v[cc], col0 + c * 32, p.delta, t, gate);
-                        }
+                        for (int cc = 0; cc < kChunksPerPart; ++cc)
+                            if (n_left - cc * 32 < 32) mask_chunk(v[cc], n_left - cc * 32);
                     }
+                    float cm[kChunksPerPart];
+#pragma unroll
+                    for (int cc = 0; cc < kChunksPerPart; ++cc) cm[cc] = chunk_max(v[cc]);
+                    float m = cm[0];
+#pragma unroll
+                    for (int cc = 1; cc < kChunksPerPart; ++cc) m = fmaxf(m, cm[cc]);
+                    if (m >= gate) {
+#pragma unroll
+                        for (int cc = 0; cc < kChunksPerPart; ++cc)
+                            if (cm[cc] >= gate) update_chunk(v[cc], cm[cc], base0 + cc * 32, p.delta, t, gate, amb);
+                    }
+                    if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
-                float va[32], vb[32];
-                if (c_beg < c_end) tmem_ld_32x32(taddr + c_beg * 32, va);
-                for (int c = c_beg; c < c_end; c += 2) {
-                    tmem_ld_wait();
-                    if (c + 1 < c_end) tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                    if (ncols - c * 32 < 32) mask_chunk(va, ncols - c * 32);
-                    if (p.dbg_scores != nullptr && row < p.n_cand) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + c * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + col0 + c * 32 + j] = va[j];
-                    }
-                    if (p.epi_mode == 1) t.b1 = fmax3(t.b1, va[0], va[31]); else if (p.epi_mode == 2) t.b1 = fmaxf(t.b1, chunk_max(va)); else
-                    process_chunk(va, col0 + c * 32, p.delta, t, gate);
-                    if (c + 1 < c_end) {
+                    // ---- general loop, one chunk at a time: diagnostics (score dump, epilogue modes) and kFuse
+                    const int ncols = ncols64 > kTileN ? kTileN : static_cast<int>(ncols64);
+                    const int n_left = ncols - h * (kChunksPerPart * 32);             // live columns of this warp's part
+                    float va[32];
+                    for (int cc = 0; cc < kChunksPerPart && cc * 32 < n_left; ++cc) {
+                        tmem_ld_32x32(taddr + cc * 32, va);
                         tmem_ld_wait();
-                        if (c + 2 < c_end) tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                        if (ncols - (c + 1) * 32 < 32) mask_chunk(vb, ncols - (c + 1) * 32);
+                        tmem_ld_fence(va);
+                        if (n_left - cc * 32 < 32) mask_chunk(va, n_left - cc * 32);
                         if (p.dbg_scores != nullptr && row < p.n_cand) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + (c + 1) * 32 + j < p.n_ref)
-                                    p.dbg_scores[row * p.n_ref + col0 + (c + 1) * 32 + j] = vb[j];
+                                if (base0 + cc * 32 + j < p.n_ref) p.dbg_scores[row * p.n_ref + base0 + cc * 32 + j] = va[j];
                         }
-                        if (p.epi_mode == 1) t.b1 = fmax3(t.b1, vb[0], vb[31]); else if (p.epi_mode == 2) t.b1 = fmaxf(t.b1, chunk_max(vb)); else
-                        process_chunk(vb, col0 + (c + 1) * 32, p.delta, t, gate);
+                        if (p.epi_mode == 1) { t.b1 = fmax3(t.b1, va[0], va[31]); continue; }
+                        const float cmx = chunk_max(va);
+                        if (p.epi_mode == 2) { t.b1 = fmaxf(t.b1, cmx); continue; }
+                        if (cmx >= gate) update_chunk(va, cmx, base0 + cc * 32, p.delta, t, gate, amb);
                     }
-                }
-                }
-                if constexpr (!kWholePart) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (kCG == 2 && !leader) mbar_arrive_leader(&t_empty[acc]);
+                        if (kCG == 2 && !leader) mbar_arrive_leader_relaxed(&t_empty[acc]);
                         else                     mbar_arrive(&t_empty[acc]);
                     }
+                    if (pr) c_gen += static_cast<unsigned long long>(clock64() - tp0);
                 }
                 ++t_it;
             }
             // ---- hand the upper column parts over, merge, emit (named barriers 1/2 among the epilogue threads)
             if (h != 0) {
-                float* mg = merge + (h - 1) * 7 * kTileM;
+                float* mg = merge + (h - 1) * 8 * kTileM;
                 if (!first_tile) named_bar_sync(2, kEW * 32);                  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
@@ -576,6 +584,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mg[4 * kTileM + r_in_tile] = __int_as_float(t.i1);
                 mg[5 * kTileM + r_in_tile] = __int_as_float(t.i2);
                 mg[6 * kTileM + r_in_tile] = __int_as_float(t.i3);
+                mg[7 * kTileM + r_in_tile] = amb;
                 __threadfence_block();
                 named_bar_arrive(1, kEW * 32);
             } else {
@@ -584,11 +593,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 int32_t oi[kParts - 1][3];
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    const float* mg = merge + pp * 7 * kTileM;
+                    const float* mg = merge + pp * 8 * kTileM;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
 #pragma unroll
                     for (int e = 0; e < 3; ++e) oi[pp][e] = __float_as_int(mg[(4 + e) * kTileM + r_in_tile]);
+                    amb = fmaxf(amb, mg[7 * kTileM + r_in_tile]);
                 }
                 named_bar_arrive(2, kEW * 32);
 #pragma unroll
@@ -602,8 +612,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 const bool valid = row < p.n_cand;
                 const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
                 const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
-                const bool flagged = valid && !p.no_recheck && (near_tie || near_thr);
-                const bool full = flagged && (t.b1 - t.b4 <= p.delta);     // four or more inside the window: full rescan
+                const bool hidden = amb > -INFINITY && amb >= t.b1 - p.delta;                 // un-inserted columns may be inside the window
+                const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hidden);
+                const bool full = flagged && (hidden || t.b1 - t.b4 <= p.delta);   // four or more inside the window: full rescan
                 if (valid) {
                     p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
                     p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
@@ -647,6 +658,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         if (pr && lane == 0) {
             p.prof[blockIdx.x * 16 + 10] = static_cast<unsigned long long>(clock64() - t_begin);
             p.prof[blockIdx.x * 16 + 11] = w_tfull;
+            p.prof[blockIdx.x * 16 + 3] = c_hot;
+            p.prof[blockIdx.x * 16 + 9] = c_gen;
         }
         // balance the last bar.arrive(2) of the lower half so no barrier state is left pending
         if (h != 0 && !first_tile) named_bar_sync(2, kEW * 32);
@@ -722,8 +735,9 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     }
     // tuning knobs (experiments only): FFR_CTA_GROUP=1|2, FFR_A_STAGES, FFR_B_STAGES
     const int sms = num_sms();
-    // cta_group::2 pays off once the B stream dominates (measured: dim 512 +10%, dim <= 256 slower)
-    int cg = env_int("FFR_CTA_GROUP", dim_pad >= 384 ? 2 : 1);
+    // cta_group::2 everywhere: half the B bytes per SM and 8 KB instead of 12 KB of shared-memory operand reads per MMA
+    // (measured: dim 128 1292 vs 1152 TFLOP/s, dim 256 1207 vs 1010, dim 512 1429 vs 1212)
+    int cg = env_int("FFR_CTA_GROUP", 2);
     if (cg != 2 || (sms & 1)) cg = 1;
     const bool fuse = cand32 != nullptr;
     if (fuse) cg = 1;
@@ -762,19 +776,12 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     p.cand32 = cand32; p.dim = dim;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-    // whole-part epilogue (TMEM stage handed back before the max tree) measured 3-6 % faster for dim >= 256, slower for
-    // short tiles (dim 128, few reference tiles)
-    const bool wp = !fuse && env_int("FFR_EPI_WHOLE", dim_pad >= 256 ? 1 : 0) != 0;   // (fused: 448 threads, no register room)
-    KernelFn fn = fuse ? filter_mma_kernel<1, 8, false, true>
-                : cg == 1 ? (wp ? filter_mma_kernel<1, 8, true, false> : filter_mma_kernel<1, 8, false, false>)
-                          : (wp ? filter_mma_kernel<2, 8, true, false> : filter_mma_kernel<2, 8, false, false>);
+    KernelFn fn = fuse ? filter_mma_kernel<1, 8, true> : cg == 1 ? filter_mma_kernel<1, 8, false> : filter_mma_kernel<2, 8, false>;
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);

@@ -18,30 +18,43 @@ namespace ffr {
 namespace {
 
 constexpr int kThreads = 256;           // 8 warps per CTA
-constexpr int kRowsPerIter = 2;
+constexpr int kRowsPerIter = 2;        // generic kernel / grid sizing; the vector kernel keeps >= 2 KB per warp in flight
 
-template <int NV>                        // float4 per lane per row: dim == 128 * NV
+// Optional second matrix (x_b, rows_b -> y16_b; fp16 output only): the filter normalises references and candidates in
+// ONE launch -- virtual rows [0, rows) are matrix a, [rows, rows + rows_b) matrix b -- and the same launch zeroes the
+// re-check header K2 appends to (zero_words 32-bit words at zero_ptr), saving a launch and a memset per call.
+struct L2Second {
+    const float* x;
+    int64_t rows;
+    __half* y16;
+    uint32_t* zero_ptr;
+    int32_t zero_words;
+};
+
+template <int NV, int kRows>             // NV float4 per lane per row (dim == 128 * NV), kRows rows in flight per warp
 __global__ void __launch_bounds__(kThreads)
-l2norm_rows_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t dim,
-                       __half* __restrict__ y16, int32_t ld16, float* __restrict__ y32,
-                       float* __restrict__ norms) {
+l2norm_rows_vec_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t dim,
+                       __half* __restrict__ y16_a, int32_t ld16, float* __restrict__ y32,
+                       float* __restrict__ norms, const L2Second sec) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
+    const int64_t rows = rows_a + sec.rows;
 
-    for (int64_t r0 = warp * kRowsPerIter; r0 < rows; r0 += nwarps * kRowsPerIter) {
-        float4 v[kRowsPerIter][NV];
+    for (int64_t r0 = warp * kRows; r0 < rows; r0 += nwarps * kRows) {
+        float4 v[kRows][NV];
 #pragma unroll
-        for (int i = 0; i < kRowsPerIter; ++i) {
+        for (int i = 0; i < kRows; ++i) {
             const int64_t r = r0 + i;
             if (r < rows) {
-                const float4* p = reinterpret_cast<const float4*>(x + r * dim);
+                const float4* p = reinterpret_cast<const float4*>(r < rows_a ? x_a + r * dim : sec.x + (r - rows_a) * dim);
 #pragma unroll
                 for (int j = 0; j < NV; ++j) v[i][j] = ldg_stream_f4(p + lane + 32 * j);
             }
         }
 #pragma unroll
-        for (int i = 0; i < kRowsPerIter; ++i) {
+        for (int i = 0; i < kRows; ++i) {
             const int64_t r = r0 + i;
             if (r >= rows) break;
             float ss = 0.f;
@@ -55,6 +68,9 @@ l2norm_rows_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t dim,
             ss = warp_sum(ss);
             const float nrm = sqrtf(ss);
             if (norms != nullptr && lane == 0) norms[r] = nrm;
+            __half* y16 = y16_a;
+            int64_t ro = r;                                         // row inside its own matrix
+            if (r >= rows_a) { y16 = sec.y16; ro = r - rows_a; }
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 float4 o;
@@ -69,12 +85,12 @@ l2norm_rows_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t dim,
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&h0);
                     pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    reinterpret_cast<uint2*>(y16 + r * ld16)[lane + 32 * j] = pk;
+                    reinterpret_cast<uint2*>(y16 + ro * ld16)[lane + 32 * j] = pk;
                 }
             }
             if (y16 != nullptr) {                                   // zero the K padding (dim..ld16)
                 for (int c = dim + lane * 4; c < ld16; c += 128)
-                    *reinterpret_cast<uint2*>(y16 + r * ld16 + c) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(y16 + ro * ld16 + c) = make_uint2(0u, 0u);
             }
         }
     }
@@ -82,14 +98,19 @@ l2norm_rows_vec_kernel(const float* __restrict__ x, int64_t rows, int32_t dim,
 
 // any dim: one warp per row, scalar accesses (row may be unaligned for float4)
 __global__ void __launch_bounds__(kThreads)
-l2norm_rows_generic_kernel(const float* __restrict__ x, int64_t rows, int32_t dim,
-                           __half* __restrict__ y16, int32_t ld16, float* __restrict__ y32,
-                           float* __restrict__ norms) {
+l2norm_rows_generic_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t dim,
+                           __half* __restrict__ y16_a, int32_t ld16, float* __restrict__ y32,
+                           float* __restrict__ norms, const L2Second sec) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
-    for (int64_t r = warp; r < rows; r += nwarps) {
-        const float* p = x + r * dim;
+    if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
+    const int64_t rows = rows_a + sec.rows;
+    for (int64_t rv = warp; rv < rows; rv += nwarps) {
+        const bool second = rv >= rows_a;
+        const int64_t r = second ? rv - rows_a : rv;
+        const float* p = second ? sec.x + r * dim : x_a + r * dim;
+        __half* y16 = second ? sec.y16 : y16_a;
         float ss = 0.f;
         for (int c = lane; c < dim; c += 32) { const float t = __ldg(p + c); ss = fmaf(t, t, ss); }
         ss = warp_sum(ss);
@@ -103,13 +124,11 @@ l2norm_rows_generic_kernel(const float* __restrict__ x, int64_t rows, int32_t di
     }
 }
 
-}  // namespace
-
-int launch_l2norm(const float* x, int64_t rows, int32_t dim, __half* y16, int32_t ld16, float* y32, float* norms,
-                  cudaStream_t s) {
-    if (rows == 0) return FFR_OK;
+static int launch_l2norm_impl(const float* x, int64_t rows, int32_t dim, __half* y16, int32_t ld16, float* y32, float* norms,
+                              const L2Second sec, cudaStream_t s) {
+    if (rows + sec.rows == 0 && sec.zero_words == 0) return FFR_OK;
     const int sms = num_sms();
-    const int64_t warps_needed = (rows + kRowsPerIter - 1) / kRowsPerIter;
+    const int64_t warps_needed = (rows + sec.rows + kRowsPerIter - 1) / kRowsPerIter;
     const int64_t blocks_needed = (warps_needed + (kThreads / 32) - 1) / (kThreads / 32);
     // up to 8 resident CTAs per SM (2048 threads); whole multiples of the SM count when the matrix is big
     int64_t grid = blocks_needed < static_cast<int64_t>(sms) * 8 ? blocks_needed : static_cast<int64_t>(sms) * 8;
@@ -117,16 +136,33 @@ int launch_l2norm(const float* x, int64_t rows, int32_t dim, __half* y16, int32_
     const bool vec_ok = (dim % 128 == 0) && (y16 == nullptr || (ld16 % 4 == 0)) &&
                         ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                         (y32 == nullptr || (reinterpret_cast<uintptr_t>(y32) & 15) == 0) &&
-                        (y16 == nullptr || (reinterpret_cast<uintptr_t>(y16) & 7) == 0);
+                        (y16 == nullptr || (reinterpret_cast<uintptr_t>(y16) & 7) == 0) &&
+                        (sec.rows == 0 || ((reinterpret_cast<uintptr_t>(sec.x) & 15) == 0 &&
+                                           (reinterpret_cast<uintptr_t>(sec.y16) & 7) == 0));
     const dim3 g(static_cast<unsigned>(grid)), b(kThreads);
-    if (vec_ok && dim == 128)       l2norm_rows_vec_kernel<1><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
-    else if (vec_ok && dim == 256)  l2norm_rows_vec_kernel<2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
-    else if (vec_ok && dim == 384)  l2norm_rows_vec_kernel<3><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
-    else if (vec_ok && dim == 512)  l2norm_rows_vec_kernel<4><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
-    else if (vec_ok && dim == 1024) l2norm_rows_vec_kernel<8><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
-    else l2norm_rows_generic_kernel<<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms);
+    if (vec_ok && dim == 128)       l2norm_rows_vec_kernel<1, 8><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 256)  l2norm_rows_vec_kernel<2, 4><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 384)  l2norm_rows_vec_kernel<3, 2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 512)  l2norm_rows_vec_kernel<4, 2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 1024) l2norm_rows_vec_kernel<8, 1><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else l2norm_rows_generic_kernel<<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
     FFR_LAUNCH_CHECK("l2norm_rows");
     return FFR_OK;
+}
+
+}  // namespace
+
+int launch_l2norm(const float* x, int64_t rows, int32_t dim, __half* y16, int32_t ld16, float* y32, float* norms,
+                  cudaStream_t s) {
+    return launch_l2norm_impl(x, rows, dim, y16, ld16, y32, norms, L2Second{nullptr, 0, nullptr, nullptr, 0}, s);
+}
+
+// fp16 normalised copies of two matrices of the same width in one launch (either may be empty), plus zero_words 32-bit
+// zeros at zero_ptr (<= 256 words)
+int launch_l2norm_pair(const float* x_a, int64_t rows_a, __half* y16_a, const float* x_b, int64_t rows_b, __half* y16_b,
+                       int32_t dim, int32_t ld16, void* zero_ptr, int32_t zero_words, cudaStream_t s) {
+    return launch_l2norm_impl(x_a, rows_a, dim, y16_a, ld16, nullptr, nullptr,
+                              L2Second{x_b, rows_b, y16_b, static_cast<uint32_t*>(zero_ptr), zero_words}, s);
 }
 
 }  // namespace ffr

@@ -45,6 +45,51 @@ __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, cons
     return __fdiv_rn(a, __fmul_rn(__fsqrt_rn(b), cc_sqrt));
 }
 
+// R consecutive reference rows at once (first row r0, row pitch dim; rows >= n_rows are clamped and their result is
+// unused): the R loads per step are independent and the 2R shuffle reductions interleave, so a warp pays one memory
+// latency and one reduction latency per R references instead of per reference -- the serial form made the few-row
+// rescan pure latency (~1000 cycles per reference).  Same arithmetic per reference as cos_fp32.
+template <int R>
+__device__ __forceinline__ void cos_fp32_multi(const float* __restrict__ c_smem, const float* __restrict__ r0, int n_rows,
+                                               int32_t dim, float cc_sqrt, int lane, bool vec, float (&out)[R]) {
+    float a[R], b[R];
+    const float* rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        a[r] = 0.f; b[r] = 0.f;
+        rp[r] = r0 + static_cast<int64_t>(r < n_rows ? r : n_rows - 1) * dim;
+    }
+    if (vec) {
+        const float4* c4 = reinterpret_cast<const float4*>(c_smem);
+        for (int k = lane; k < (dim >> 2); k += 32) {
+            const float4 cv = c4[k];
+            float4 rv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) rv[r] = __ldg(reinterpret_cast<const float4*>(rp[r]) + k);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                a[r] = fmaf(cv.x, rv[r].x, a[r]); a[r] = fmaf(cv.y, rv[r].y, a[r]);
+                a[r] = fmaf(cv.z, rv[r].z, a[r]); a[r] = fmaf(cv.w, rv[r].w, a[r]);
+                b[r] = fmaf(rv[r].x, rv[r].x, b[r]); b[r] = fmaf(rv[r].y, rv[r].y, b[r]);
+                b[r] = fmaf(rv[r].z, rv[r].z, b[r]); b[r] = fmaf(rv[r].w, rv[r].w, b[r]);
+            }
+        }
+    } else {
+        for (int k = lane; k < dim; k += 32) {
+            const float cv = c_smem[k];
+            float rv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) rv[r] = __ldg(rp[r] + k);
+#pragma unroll
+            for (int r = 0; r < R; ++r) { a[r] = fmaf(cv, rv[r], a[r]); b[r] = fmaf(rv[r], rv[r], b[r]); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { a[r] = warp_sum(a[r]); b[r] = warp_sum(b[r]); }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = __fdiv_rn(a[r], __fmul_rn(__fsqrt_rn(b[r]), cc_sqrt));
+}
+
 __device__ __forceinline__ void emit_result(int32_t row, float best, int32_t bi, float thr, int64_t ref_index_base,
                                             uint8_t* keep, int32_t* best_idx, float* best_val, float band_tol,
                                             int32_t* band_count, int64_t* band_rows, int64_t band_cap) {
@@ -57,13 +102,12 @@ __device__ __forceinline__ void emit_result(int32_t row, float best, int32_t bi,
     }
 }
 
-// K3a: near-tie / near-threshold rows -- fp32 cosine against the one or two leading references. One warp per row.
-__global__ void __launch_bounds__(kThreads)
-recheck_pairs_kernel(const float* __restrict__ ref, const float* __restrict__ cand, int32_t dim, float thr,
-                     int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
-                     float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
-                     int64_t* band_rows, int64_t band_cap, int vec) {
-    extern __shared__ __align__(16) float s_rows[];            // kWarps x dim
+// K3a: near-tie / near-threshold rows -- fp32 cosine against the one to three leading references. One warp per row.
+__device__ __forceinline__ void
+recheck_pairs_phase(float* s_rows, const float* __restrict__ ref, const float* __restrict__ cand, int32_t dim, float thr,
+                    int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+                    float* __restrict__ best_val, const RecheckLists& lists, float band_tol, int32_t* band_count,
+                    int64_t* band_rows, int64_t band_cap, bool vec) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* c_smem = s_rows + static_cast<size_t>(w) * dim;
     int64_t count = lists.hdr->recheck_count;
@@ -78,15 +122,14 @@ recheck_pairs_kernel(const float* __restrict__ ref, const float* __restrict__ ca
         for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
         __syncwarp();
         const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
-        float best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec != 0);
+        float best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec);
         int32_t bi = rec.idx1;
-        if (rec.idx2 >= 0) {
-            const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec != 0);
+        if (rec.idx2 >= 0) {                                     // the second and third candidate in flight together
+            const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec);
+            const float s3 = rec.idx3 >= 0 ? cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx3) * dim, dim, cc_sqrt, lane, vec)
+                                           : -INFINITY;
             if (s2 > best || (s2 == best && rec.idx2 < bi)) { best = s2; bi = rec.idx2; }
-        }
-        if (rec.idx3 >= 0) {
-            const float s3 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx3) * dim, dim, cc_sqrt, lane, vec != 0);
-            if (s3 > best || (s3 == best && rec.idx3 < bi)) { best = s3; bi = rec.idx3; }
+            if (rec.idx3 >= 0 && (s3 > best || (s3 == best && rec.idx3 < bi))) { best = s3; bi = rec.idx3; }
         }
         if (lane == 0)
             emit_result(rec.row, best, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
@@ -116,19 +159,96 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
 // fixed grid (the flagged-row count only exists on the device); n_slices slices merge into one result per row.
 constexpr int kSliceRefs = 1024;
 
+// K3b, few rows: when (flagged rows x references) is small the tiled walk below is pure latency (one block crawls through
+// a whole 1024-reference slice for a handful of rows: ~25 us at 1k references).  Here every warp of the grid takes
+// (row, block of kSmallRefs references) items instead: the row is parked in this warp's shared-memory slot, lanes split
+// the embedding, one fp32 cosine per reference exactly like K3a (kSmallBatch references in flight).  Same merge: atomicMax on the packed key, and the
+// last item of a group of kFullGroup rows (full_ctr counts rows x blocks) writes the group's outputs.
+constexpr int kSmallRefs = 32;
+constexpr int kSmallBatch = 8;
+constexpr long long kSmallPairs = 2000000;
+
+__device__ __forceinline__ void
+rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
+                   float thr, int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+                   float* __restrict__ best_val, const RecheckLists& lists, int64_t count, float band_tol,
+                   int32_t* band_count, int64_t* band_rows, int64_t band_cap, bool vec) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* c_smem = s_rows + static_cast<size_t>(w) * dim;
+    const int64_t nb = (n_ref + kSmallRefs - 1) / kSmallRefs;
+    const int64_t n_items = count * nb;
+    const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t parked = -1;
+    float cc_sqrt = 0.f;
+    for (int64_t item = warp; item < n_items; item += nwarps) {
+        const int64_t slot = item / nb, blk = item - slot * nb;
+        if (slot != parked) {
+            const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
+            float cc = 0.f;
+            __syncwarp();
+            for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+            __syncwarp();
+            cc_sqrt = __fsqrt_rn(warp_sum(cc));
+            parked = slot;
+        }
+        const int64_t lo = blk * kSmallRefs;
+        const int64_t hi = (lo + kSmallRefs < n_ref) ? lo + kSmallRefs : n_ref;
+        float best = -INFINITY;
+        int32_t bi = 0x7FFFFFFF;
+        for (int64_t i = lo; i < hi; i += kSmallBatch) {         // ascending + strict '>' = first occurrence
+            float sc[kSmallBatch];
+            const int n_rows = static_cast<int>(hi - i < kSmallBatch ? hi - i : kSmallBatch);
+            cos_fp32_multi<kSmallBatch>(c_smem, ref + i * dim, n_rows, dim, cc_sqrt, lane, vec, sc);
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r)
+                if (r < n_rows && sc[r] > best) { best = sc[r]; bi = static_cast<int32_t>(i + r); }
+        }
+        if (lane == 0 && bi != 0x7FFFFFFF) atomicMax(&lists.full_keys[slot], pack_key(best, bi));
+        __threadfence();
+        const int64_t g = slot / kFullGroup;
+        const int64_t rows_in_g = (count - g * kFullGroup < kFullGroup) ? count - g * kFullGroup : kFullGroup;
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&lists.full_ctr[g], 1) == static_cast<int>(rows_in_g * nb) - 1) ? 1 : 0;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < rows_in_g) {
+            __threadfence();
+            const int64_t sl = g * kFullGroup + lane;
+            const unsigned long long key = atomicAdd(&lists.full_keys[sl], 0ull);      // coherent read
+            float v;
+            int32_t bidx;
+            unpack_key(key, v, bidx);
+            if (key == 0ull) { v = -INFINITY; bidx = 0; }
+            emit_result(lists.full_rows[sl], v, bidx, thr, ref_index_base, keep, best_idx, best_val, band_tol,
+                        band_count, band_rows, band_cap);
+        }
+    }
+}
+
+// One launch re-checks everything K2 flagged: phase A = K3a (pairs list), phase B = K3b (full-rescan list; small or
+// tiled walk, chosen from the device-side count, uniform over the grid).  The phases touch disjoint rows.
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
-rescan_full_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
-                   int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
-                   float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
-                   int64_t* band_rows, int64_t band_cap) {
+recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
+               int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+               float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
+               int64_t* band_rows, int64_t band_cap) {
     extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows | staged reference tile
     __shared__ float s_ccs[kFullGroup];
     __shared__ unsigned long long s_key[kWarps][kFullGroup];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
+                        band_rows, band_cap, kVec);
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
+    if (count == 0) return;
+    if (static_cast<long long>(count) * n_ref <= kSmallPairs) {
+        rescan_small_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, count, band_tol,
+                           band_count, band_rows, band_cap, kVec);
+        return;
+    }
+    __syncthreads();                                            // phase A's per-warp rows are dead: the tiled walk reuses s_c
     const int64_t n_slices = (n_ref + kSliceRefs - 1) / kSliceRefs;
     const int64_t n_groups = (count + kFullGroup - 1) / kFullGroup;
     const int64_t n_items = n_groups * n_slices;
@@ -337,31 +457,20 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     const size_t smem = static_cast<size_t>(kWarps) * dim * sizeof(float);
     if (smem > 48 * 1024) { set_error("recheck: dim %d too large", dim); return FFR_ERR_UNSUPPORTED; }
     const int vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(ref) & 15) == 0);
-    // the flagged-row counts live on the device; fixed grids stride over them (idle blocks exit at once)
-    int64_t grid = (n_cand + kWarps - 1) / kWarps;
-    if (grid > static_cast<int64_t>(sms) * 4) grid = static_cast<int64_t>(sms) * 4;
-    recheck_pairs_kernel<<<static_cast<unsigned>(grid), kThreads, smem, s>>>(ref, cand, dim, thr, ref_index_base, keep,
-                                                                             idx, val, lists, band_tol, band_count,
-                                                                             band_rows, band_cap, vec);
-    FFR_LAUNCH_CHECK("recheck_pairs");
-    // full rescans: (row group, 512-reference slice) work items round-robin over a fixed grid
-    const int64_t groups = (n_cand + kFullGroup - 1) / kFullGroup;
-    const int64_t items = groups * ((n_ref + kSliceRefs - 1) / kSliceRefs);
-    int64_t gx = static_cast<int64_t>(sms) * 2;               // two blocks per SM are resident (registers): one wave
-    if (gx > items) gx = items;
-    if (gx < 1) gx = 1;
+    // the flagged-row counts live on the device: ONE fixed grid strides over both lists (blocks without work exit at once)
+    const int64_t gx = static_cast<int64_t>(sms) * 2;         // two blocks per SM are resident (registers): one wave
     const dim3 g2(static_cast<unsigned>(gx));
     const size_t smem_full = smem + static_cast<size_t>(kTileRefs) * kKCPad * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(rescan_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    if (vec) rescan_full_kernel<true><<<g2, kThreads, smem_full, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                                                  lists, band_tol, band_count, band_rows, band_cap);
-    else     rescan_full_kernel<false><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                                                   lists, band_tol, band_count, band_rows, band_cap);
-    FFR_LAUNCH_CHECK("rescan_full");
+    if (vec) recheck_kernel<true><<<g2, kThreads, smem_full, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                                              lists, band_tol, band_count, band_rows, band_cap);
+    else     recheck_kernel<false><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                                               lists, band_tol, band_count, band_rows, band_cap);
+    FFR_LAUNCH_CHECK("recheck");
     return FFR_OK;
 }
 

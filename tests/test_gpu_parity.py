@@ -230,7 +230,7 @@ def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
     monkeypatch.setenv("FFR_FUSE_K1", "1")
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + n_ref, n_adversarial=100, n_dup_refs=8, unit_norm=False)
     res = _check_cosine(ops, ref, cand, 0.5)
-    assert res.stats["launches"] == 4                      # K1(ref) + K2 + K3a + K3b: no K1 over the candidates
+    assert res.stats["launches"] == 3                      # K1(references only) + K2 + K3: no K1 pass over the candidates
 
 
 def test_filter_mma_config2_full(ops):

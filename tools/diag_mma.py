@@ -97,6 +97,9 @@ def prof(n_ref, n_cand, dim):
           f"t_empty {ml[6] / ml[4]:.1%}, b_full {ml[7] / ml[4]:.1%}")
     print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
           f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
+    if m[3] + m[9] + m[15] > 0:
+        print(f"      epilogue w4 per ref tile: wait->first chunk loaded {m[3] / tiles:.0f}, chunk loop {m[9] / tiles:.0f}, "
+              f"fence+arrive {m[15] / tiles:.0f} cyc", flush=True)
     if m[12] > 0:
         print(f"    converter 0: total {m[12]:.3e} cyc; waiting a_empty {m[13] / m[12]:.1%}; busy {(m[12] - m[13]) / max(m[14], 1):.0f} cyc "
               f"per candidate tile ({m[14]:.0f} tiles)", flush=True)
@@ -127,7 +130,15 @@ if __name__ == "__main__":
         prof(100_000, 300_000, 128)
         prof(1000, 100_000, 128)
         prof(256, 2_000_000, 128)
+    if "--prof128" in sys.argv:
+        prof(100_000, 300_000, 128)
+        prof(1000, 100_000, 128)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
         perf(8, 10_000_000, 128)
+    if "--perf2" in sys.argv:
+        perf(1000, 100_000, 128, flags=ops.FLAG_NO_RECHECK)
+        perf(100_000, 1_250_000, 128, flags=ops.FLAG_NO_RECHECK, iters=2)
+        perf(10_000, 500_000, 256, flags=ops.FLAG_NO_RECHECK, iters=3)
+        perf(10_000, 1_000_000, 512, flags=ops.FLAG_NO_RECHECK, iters=3)
