@@ -137,7 +137,7 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
 
     const int32_t ld = ffr_padded_dim(dim);
     const __half* ref16 = ref16_pre;
-    const __half* cand16 = nullptr;
+    __half* cand16 = nullptr;
     const float* fuse_cand = nullptr;        // non-null: K2 normalises the candidates itself (K1 fused)
     int launches = 0;
     int rc;
@@ -145,9 +145,10 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         // K1: references (unless the caller cached them) and candidates in ONE launch, which also zeroes the header
         static_assert(sizeof(WsHeader) % 4 == 0 && sizeof(WsHeader) / 4 <= 256, "header is zeroed by one CTA");
         __half* r16 = ref16 == nullptr ? reinterpret_cast<__half*>(ws + L.ref16) : nullptr;
-        fuse_cand = filter_mma_can_fuse(static_cast<const float*>(cand), dim, ld) ? static_cast<const float*>(cand) : nullptr;
-        __half* c16 = fuse_cand == nullptr ? reinterpret_cast<__half*>(ws + L.cand16) : nullptr;
-        rc = launch_l2norm_pair(c16 ? static_cast<const float*>(cand) : nullptr, c16 ? n_cand : 0, c16,
+        fuse_cand = filter_mma_can_fuse(static_cast<const float*>(cand), n_ref, n_cand, dim, ld) ? static_cast<const float*>(cand) : nullptr;
+        __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
+        const bool k1_cand = fuse_cand == nullptr;          // otherwise K2's normaliser warps write c16 themselves
+        rc = launch_l2norm_pair(k1_cand ? static_cast<const float*>(cand) : nullptr, k1_cand ? n_cand : 0, c16,
                                 r16 ? static_cast<const float*>(ref) : nullptr, r16 ? n_ref : 0, r16, dim, ld, hdr,
                                 static_cast<int32_t>(sizeof(WsHeader) / 4), s);
         if (rc != FFR_OK) return rc;
@@ -156,7 +157,7 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         cand16 = c16;
     } else {
         if (ref16 == nullptr) ref16 = static_cast<const __half*>(ref);
-        cand16 = static_cast<const __half*>(cand);
+        cand16 = const_cast<__half*>(static_cast<const __half*>(cand));      // fp16 input: only read
     }
     const bool recheck = (dtype == FFR_DTYPE_F32) && !(flags & FFR_FLAG_NO_RECHECK);
     g_last.launches = launches + 1 + (recheck ? 1 : 0);

@@ -92,6 +92,17 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_shared_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -236,8 +247,8 @@ int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64
                        float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
 int launch_l2norm_pair(const float* x_a, int64_t rows_a, __half* y16_a, const float* x_b, int64_t rows_b, __half* y16_b,
                        int32_t dim, int32_t ld16, void* zero_ptr, int32_t zero_words, cudaStream_t s);
-bool filter_mma_can_fuse(const float* cand32, int32_t dim, int32_t dim_pad);
-int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, const float* cand32, int32_t dim,
+bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int32_t dim, int32_t dim_pad);
+int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, cudaStream_t s);

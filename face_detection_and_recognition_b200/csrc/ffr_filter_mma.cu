@@ -216,19 +216,22 @@ struct KParams {
     RecheckLists lists;
     int no_recheck;
     float* dbg_scores;
-    const float* cand32;           // kFuse: original fp32 candidate rows [n_cand, dim]
-    int32_t dim;                   // kFuse: true embedding size (row pitch of cand32)
+    const float* cand32;           // kNorm: original fp32 candidate rows [n_cand, dim]
+    __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
+    int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
     unsigned long long* prof;      // optional [gridDim.x][16] stall-cycle counters (diagnostics)
 };
 
-// kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8|16) = 4 TMEM lane quadrants x kEW/4 column parts.
-// kFuse: the A (candidate) tile is produced in-kernel from the fp32 rows by four extra "converter" warps (row L2
-// normalisation + fp16 cast + 128-byte-swizzled store) instead of TMA-loading K1's fp16 copy: candidates are read
-// from HBM once, as fp32, and never written back.  Used when the A ring has >= 2 stages (dim <= 256).
-template <int kCG, int kEW, bool kFuse>
-__global__ void __launch_bounds__(64 + 32 * kEW + (kFuse ? 128 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
+// kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8) = 4 TMEM lane quadrants x kEW/4 column parts.
+// kNorm: K1 for the candidates runs INSIDE this kernel.  Two extra "normaliser" warps (the hardware allocates warps in
+// fours, so 10 warps cost 12 anyway) read the fp32 rows of the CTA's NEXT candidate tile, L2-normalise them exactly like K1
+// and write the fp16 rows into the workspace, while the tensor core works on the current tile; the TMA producer waits
+// for a per-CTA counter before it loads a tile.  The rows come back through L2, HBM sees the fp32 embeddings once, and
+// the 0.6 ms K1 pass over 1.25 M x 512 disappears behind the MMAs (the kernel needs < 10 % of K1's bandwidth).
+template <int kCG, int kEW, bool kNorm>
+__global__ void __launch_bounds__(64 + 32 * kEW + (kNorm ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const KParams p) {
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
@@ -247,6 +250,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint32_t* norm_count = tmem_slot + 1;                            // kNorm: [2] candidate tiles finished by each normaliser warp
     float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
 
     const int warp = threadIdx.x >> 5;
@@ -261,7 +265,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         tma_prefetch_desc(&tmap_cand);
         tma_prefetch_desc(&tmap_ref);
-        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], kFuse ? 4 * kCG : 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        norm_count[0] = 0; norm_count[1] = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
         fence_barrier_init();
@@ -283,23 +288,26 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         {
             uint32_t a_it = 0, b_it = 0;
             const bool pr = p.prof != nullptr;
-            unsigned long long w_aempty = 0, w_bempty = 0;
+            unsigned long long w_aempty = 0, w_bempty = 0, w_norm = 0;
             const long long t_begin = clock64();
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
                 const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
                 const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
-                if constexpr (!kFuse) {
-                    mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_aempty);
-                    if (elect_one()) {
-                        if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
-                        for (int kb = 0; kb < p.kb_count; ++kb) {
-                            uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
-                            if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
-                            else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
-                        }
-                    }
-                    __syncwarp();
+                if constexpr (kNorm) {                      // this tile's fp16 rows must have been written (both warps)
+                    const long long tn0 = pr ? clock64() : 0;
+                    while (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it) { }
+                    if (pr) w_norm += static_cast<unsigned long long>(clock64() - tn0);
                 }
+                mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_aempty);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
+                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                        else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                    }
+                }
+                __syncwarp();
                 ++a_it;
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const int32_t rrow0 = rt * kTileN + static_cast<int32_t>(cta_rank * kBRows);
@@ -321,6 +329,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 p.prof[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
                 p.prof[blockIdx.x * 16 + 1] = w_aempty;
                 p.prof[blockIdx.x * 16 + 2] = w_bempty;
+                p.prof[blockIdx.x * 16 + 12] = w_norm;
             }
         }
     } else if (warp == 1) {
@@ -389,93 +398,76 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 p.prof[blockIdx.x * 16 + 8] = t_it;
             }
         }
-    } else if (kFuse && warp >= 2 + kEW) {
-        // ===================== converter warps: fp32 rows -> normalised fp16 A tile (K1 fused) =====================
-        // Warp cw owns rows [32 cw, 32 cw + 32) of the tile.  One row at a time, lane l holds float4 #(l + 32 j) of
-        // the row (coalesced 512-byte loads, eight rows in flight), the warp reduces the sum of squares, scales by
-        // rsqrt and stores 8 bytes per float4 into the K-major
-        // SWIZZLE_128B layout the UMMA descriptor expects: 16-byte chunk index XOR (row & 7) inside each 128-byte row.
-        const int cw = warp - (2 + kEW);
+    } else if (kNorm && warp >= 2 + kEW) {
+        // ===================== normaliser warps: fp32 rows -> L2-normalised fp16 rows in the workspace (K1 in-kernel) ====
+        // Warp nw of 2 owns rows nw*4 .. nw*4+3 of every group of 8 rows of the CTA's tile; one row at a time per lane
+        // set: lane l holds float4 #(l + 32 j) of the row (coalesced 512-byte loads, four rows = up to 8 KB in flight per
+        // warp), warp-shuffle sum of squares, IEEE sqrt and one division per row, 8-byte fp16 stores.  The tiles are taken in
+        // the order the TMA producer will load them; nothing else is waited for (the fp16 rows of different tiles are
+        // different memory), so the warps run ahead of the tensor core by as much as their bandwidth allows.
+        const int nw = warp - (2 + kEW);
         const int nvec = p.dim >> 2;                                   // float4 per row (dim % 4 == 0 checked on the host)
-        constexpr int kRowsAhead = 8;                                 // 8 rows (4-8 KB) in flight per warp
-        uint32_t a_it = 0;
-        const bool pr = p.prof != nullptr && cw == 0;
-        unsigned long long w_cv_aempty = 0;
-        const long long t_cv_begin = clock64();
+        const int ld16 = p.kb_count * kBlockK;
+        constexpr int kR = 4;                                         // rows in flight per warp
+        const bool pr = p.prof != nullptr && nw == 0;
+        const long long t_nv_begin = clock64();
+        uint32_t n_done = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-            const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
-            const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM + cw * 32;
-            mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_cv_aempty);
-            uint8_t* a_base = smem_a + as * a_stage_bytes;
-            for (int rb = 0; rb < 32; rb += kRowsAhead) {
-                float4 v[kRowsAhead][2];
-                // all loads first, unconditionally (addresses clamped into the matrix), so that they are all in flight
-                // before the first one is consumed; out-of-range pieces are zeroed afterwards
+            const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
+            for (int rb = nw * kR; rb < kTileM; rb += 2 * kR) {
+                if (row0 + rb >= p.n_cand) break;
+                float4 v[kR][4];
 #pragma unroll
-                for (int u = 0; u < kRowsAhead; ++u) {
+                for (int u = 0; u < kR; ++u) {
                     int64_t gr = row0 + rb + u;
-                    gr = gr < p.n_cand ? gr : p.n_cand - 1;
+                    gr = gr < p.n_cand ? gr : p.n_cand - 1;            // clamped: loads stay unconditional and in flight together
+                    const float4* src = reinterpret_cast<const float4*>(p.cand32 + gr * p.dim);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        int f = lane + 32 * j;
-                        f = f < nvec ? f : nvec - 1;
-                        if (j == 0 || nvec > 32) v[u][j] = ldg_stream_f4(reinterpret_cast<const float4*>(p.cand32 + gr * p.dim) + f);
-                        else                     v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = lane + 32 * j;
+                        v[u][j] = (f < nvec) ? ldg_stream_f4(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kRowsAhead; ++u) {
-                    const bool live_row = (row0 + rb + u) < p.n_cand;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (!live_row || lane + 32 * j >= nvec) v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < kRowsAhead; ++u) {
+                for (int u = 0; u < kR; ++u) {
+                    const int64_t gr = row0 + rb + u;
                     float ss = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         ss = fmaf(v[u][j].x, v[u][j].x, ss); ss = fmaf(v[u][j].y, v[u][j].y, ss);
                         ss = fmaf(v[u][j].z, v[u][j].z, ss); ss = fmaf(v[u][j].w, v[u][j].w, ss);
                     }
                     ss = warp_sum(ss);
-                    // 1/|x| by MUFU.RSQ and one multiply per element (within 2 ulp of K1's IEEE sqrt + divide, far below
-                    // the fp16 rounding that follows): these four warps have no spare latency for division sequences
-                    const float inv = rsqrtf(ss);
-                    const int r = cw * 32 + rb + u;                    // row inside the tile
-                    const bool live = (row0 + rb + u) < p.n_cand;
+                    // one IEEE division per row, then multiplies: 16 division sequences per row and lane made these two warps
+                    // ALU bound (118 k cycles per 128 x 512 tile).  <= 1.5 ulp from K1's x / |x| before the fp16 rounding.
+                    const float inv = __fdiv_rn(1.0f, sqrtf(ss));
+                    if (gr < p.n_cand) {
+                        __half* dst = p.cand16 + gr * ld16;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int f = lane + 32 * j;                   // float4 index -> columns 4f .. 4f+3
-                        if (4 * f < p.kb_count * kBlockK) {
-                            uint2 pk = make_uint2(0u, 0u);
-                            if (live && f < nvec) {
-                                const __half2 h0 = __floats2half2_rn(v[u][j].x * inv, v[u][j].y * inv);
-                                const __half2 h1 = __floats2half2_rn(v[u][j].z * inv, v[u][j].w * inv);
-                                pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-                                pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        for (int j = 0; j < 4; ++j) {
+                            const int f = lane + 32 * j;
+                            if (4 * f < ld16) {                        // columns [dim, ld16) are the zero K padding
+                                uint2 pk = make_uint2(0u, 0u);
+                                if (f < nvec) {
+                                    const __half2 h0 = __floats2half2_rn(v[u][j].x * inv, v[u][j].y * inv);
+                                    const __half2 h1 = __floats2half2_rn(v[u][j].z * inv, v[u][j].w * inv);
+                                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                }
+                                reinterpret_cast<uint2*>(dst)[f] = pk;
                             }
-                            const int kb = f >> 4;                     // 16 float4 = 64 columns per K-block
-                            const int chunk = (f & 15) >> 1;           // 16-byte chunk inside the 128-byte row
-                            const int within = (f & 1) * 8;
-                            uint8_t* dst = a_base + kb * kABlockBytes + r * 128 + ((chunk ^ (r & 7)) << 4) + within;
-                            *reinterpret_cast<uint2*>(dst) = pk;
                         }
                     }
                 }
             }
-            fence_proxy_async_smem();                                   // generic-proxy stores -> visible to tcgen05.mma
+            fence_proxy_async_global();                                 // generic-proxy stores -> visible to the TMA loads
             __syncwarp();
-            if (lane == 0) {
-                if (kCG == 2 && !leader) mbar_arrive_leader(&a_full[as]);
-                else                     mbar_arrive(&a_full[as]);
-            }
-            ++a_it;
+            if (lane == 0) red_release_shared_add(&norm_count[nw], 1u);
+            ++n_done;
         }
         if (pr && lane == 0) {
-            p.prof[blockIdx.x * 16 + 12] = static_cast<unsigned long long>(clock64() - t_cv_begin);
-            p.prof[blockIdx.x * 16 + 13] = w_cv_aempty;
-            p.prof[blockIdx.x * 16 + 14] = a_it;
+            p.prof[blockIdx.x * 16 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
+            p.prof[blockIdx.x * 16 + 14] = n_done;
         }
     } else {
         // ===================== epilogue: one thread per (candidate row, column half) =====================
@@ -487,7 +479,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
-        const bool hot_ok = !kFuse && p.dbg_scores == nullptr && p.epi_mode == 0;
+        const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -544,7 +536,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     }
                     if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
-                    // ---- general loop, one chunk at a time: diagnostics (score dump, epilogue modes) and kFuse
+                    // ---- general loop, one chunk at a time: diagnostics only (score dump, epilogue modes)
                     const int ncols = ncols64 > kTileN ? kTileN : static_cast<int>(ncols64);
                     const int n_left = ncols - h * (kChunksPerPart * 32);             // live columns of this warp's part
                     float va[32];
@@ -720,8 +712,8 @@ int a_stage_count(int32_t dim_pad) {
     return a_stage <= 32768 ? 3 : (a_stage <= 65536 ? 2 : 1);
 }
 
-// cand32 != nullptr: fuse the candidates' normalisation into the kernel (cand16 is then ignored)
-int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* cand16, const float* cand32, int32_t dim,
+// cand32 != nullptr: the candidates' normalisation runs inside the kernel, which then WRITES cand16 (workspace) itself
+int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                            int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                            RecheckLists lists, int no_recheck, float* dbg_scores, cudaStream_t s) {
@@ -740,15 +732,13 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     int cg = env_int("FFR_CTA_GROUP", 2);
     if (cg != 2 || (sms & 1)) cg = 1;
     const bool fuse = cand32 != nullptr;
-    if (fuse) cg = 1;
     const int kb = dim_pad / kBlockK;
     const uint32_t a_stage = kb * kABlockBytes;
     const uint32_t b_stage = (kTileN / cg) * kBlockK * 2;
-    int a_stages = a_stage_count(dim_pad);
-    if (!fuse) a_stages = env_int("FFR_A_STAGES", a_stages);
+    int a_stages = env_int("FFR_A_STAGES", a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
-    const int ew = 8;      // 16 epilogue warps were measured: no gain (the TMEM read path, not latency, bounds pass 1)
+    const int ew = 8;      // 16 epilogue warps were measured: no gain
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     const uint32_t budget = kSmemLimit - extra;
     while (a_stages > 1 && a_stages * a_stage + 2 * b_stage > budget) --a_stages;
@@ -762,26 +752,25 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     CUtensorMap tm_c, tm_r;
     int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN / cg);
     if (rc != FFR_OK) return rc;
-    if (fuse) tm_c = tm_r;                                   // unused by the fused kernel
-    else {
-        rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
-        if (rc != FFR_OK) return rc;
-    }
+    rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
+    if (rc != FFR_OK) return rc;
 
     KParams p;
     p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
     p.thr = thr; p.delta = delta; p.thr_band = thr_band; p.ref_index_base = ref_index_base;
     p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
     p.acc_stages = env_int("FFR_ACC_STAGES", 2) == 1 ? 1 : 2;
-    p.cand32 = cand32; p.dim = dim;
+    p.cand32 = cand32; p.cand16 = cand16; p.dim = dim;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-    KernelFn fn = fuse ? filter_mma_kernel<1, 8, true> : cg == 1 ? filter_mma_kernel<1, 8, false> : filter_mma_kernel<2, 8, false>;
+    KernelFn fn = cg == 1 ? (fuse ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)
+                          : (fuse ? filter_mma_kernel<2, 8, true> : filter_mma_kernel<2, 8, false>);
     static bool attr_set = false;
     if (!attr_set) {
         FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);
@@ -789,7 +778,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
     const unsigned grid = static_cast<unsigned>((n_tiles < max_groups ? n_tiles : max_groups) * cg);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(64 + 32 * ew + (fuse ? 128 : 0));
+    cfg.blockDim = dim3(64 + 32 * ew + (fuse ? 64 : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -804,16 +793,23 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, const __half* can
 
 }  // namespace
 
-// true when ffr_filter may skip K1 for the candidates and let K2 normalise them in-kernel.  OFF by default: measured
-// slower than K1 + K2 -- four converter warps keep only ~16 KB of HBM loads in flight per SM (0.64 TB/s against K1's
-// 6.2 TB/s with 64 warps per SM), and shared memory has no room for a deep fp32 staging ring next to the A and B tiles.
-// FFR_FUSE_K1=1 enables it (tests/test_gpu_parity.py::test_fused_normalisation_path keeps it correct).
-bool filter_mma_can_fuse(const float* cand32, int32_t dim, int32_t dim_pad) {
-    return env_int("FFR_FUSE_K1", 0) != 0 && cand32 != nullptr && (dim % 4) == 0 && dim <= 256 &&
-           (reinterpret_cast<uintptr_t>(cand32) & 15) == 0 && a_stage_count(dim_pad) >= 2;
+// true when ffr_filter skips the K1 pass over the candidates and lets K2's normaliser warps do it behind the MMAs.
+// That needs float4-addressable rows and enough tensor work per candidate tile to hide two warps' worth of loads
+// (~8 GB/s per SM): with few reference tiles per candidate tile the kernel would wait for its own normaliser, and the
+// separate full-bandwidth K1 pass is the better schedule.  FFR_FUSE_K1=0|1 forces the choice (tests).
+bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int32_t dim, int32_t dim_pad) {
+    if (cand32 == nullptr || (dim % 4) != 0 || (reinterpret_cast<uintptr_t>(cand32) & 15) != 0) return false;
+    const int forced = env_int("FFR_FUSE_K1", -1);
+    if (forced >= 0) return forced != 0;
+    // Tensor time per candidate tile ~ n_rt * (dim_pad / 64) * 512 cycles; the two normaliser warps keep <= 16 KB in flight per
+    // SM (~7 B/cycle against HBM latency), i.e. ~75 * dim cycles per 128-row tile: hidden with 2x margin from ~20 reference
+    // tiles up, whatever the dim.  Few candidate tiles per CTA would expose the first tile's un-hidden pass instead.
+    const int64_t n_rt = (n_ref + kTileN - 1) / kTileN;
+    (void)dim_pad;
+    return n_rt >= 24 && n_cand >= 4 * static_cast<int64_t>(kTileM) * num_sms();
 }
 
-int launch_filter_mma(const __half* ref16, int64_t n_ref, const __half* cand16, const float* cand32, int32_t dim,
+int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, cudaStream_t s) {
@@ -827,7 +823,7 @@ void set_mma_prof_buffer(unsigned long long* dev_ptr) { g_prof = dev_ptr; }
 int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                             float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                             float* scores, cudaStream_t s) {
-    return launch_filter_mma_impl(ref16, n_ref, cand16, nullptr, dim_pad, n_cand, dim_pad, thr, delta, delta, 0, keep, idx,
+    return launch_filter_mma_impl(ref16, n_ref, const_cast<__half*>(cand16), nullptr, dim_pad, n_cand, dim_pad, thr, delta, delta, 0, keep, idx,
                                   val, lists, 0, scores, s);
 }
 

@@ -223,14 +223,23 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
         assert res.stats["rechecked"] >= 900
 
 
-@pytest.mark.parametrize("n_ref,n_cand,dim", [(300, 5000, 128), (1000, 3001, 256), (64, 700, 64), (500, 129, 192)])
+@pytest.mark.parametrize("n_ref,n_cand,dim", [(300, 5000, 128), (1000, 3001, 256), (64, 700, 64), (500, 129, 192),
+                                              (300, 60_000, 128), (700, 45_000, 512), (257, 40_001, 320)])
 def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
-    """Experimental K2 variant that normalises the fp32 candidates in-kernel (FFR_FUSE_K1=1, off by default because it
-    is slower): same parity bar as the default K1 + K2 path."""
-    monkeypatch.setenv("FFR_FUSE_K1", "1")
+    """K2 with in-kernel normalisation of the candidates (two normaliser warps write the fp16 rows of the CTA's next tile
+    into the workspace while the tensor core works; default for large reference sets, forced here with FFR_FUSE_K1=1):
+    same parity bar as K1 + K2, and the same decisions as the K1 + K2 schedule."""
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + n_ref, n_adversarial=100, n_dup_refs=8, unit_norm=False)
+    monkeypatch.setenv("FFR_FUSE_K1", "1")
     res = _check_cosine(ops, ref, cand, 0.5)
     assert res.stats["launches"] == 3                      # K1(references only) + K2 + K3: no K1 pass over the candidates
+    monkeypatch.setenv("FFR_FUSE_K1", "0")
+    import torch
+    r2 = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, band_tol=1e-3)
+    # the two schedules differ by <= 1 fp16 ulp in rare operand elements (x * (1/|x|) vs x / |x|): same decisions
+    assert (res.best_idx != r2.best_idx).float().mean().item() < 1e-3
+    assert (res.keep != r2.keep).float().mean().item() < 1e-3
+    assert (res.best_val - r2.best_val).abs().max().item() < 1e-3
 
 
 def test_filter_mma_config2_full(ops):

@@ -97,12 +97,11 @@ def prof(n_ref, n_cand, dim):
           f"t_empty {ml[6] / ml[4]:.1%}, b_full {ml[7] / ml[4]:.1%}")
     print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
           f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
-    if m[3] + m[9] + m[15] > 0:
-        print(f"      epilogue w4 per ref tile: wait->first chunk loaded {m[3] / tiles:.0f}, chunk loop {m[9] / tiles:.0f}, "
-              f"fence+arrive {m[15] / tiles:.0f} cyc", flush=True)
-    if m[12] > 0:
-        print(f"    converter 0: total {m[12]:.3e} cyc; waiting a_empty {m[13] / m[12]:.1%}; busy {(m[12] - m[13]) / max(m[14], 1):.0f} cyc "
-              f"per candidate tile ({m[14]:.0f} tiles)", flush=True)
+    if m[3] + m[9] > 0:
+        print(f"      epilogue w4 per ref tile: hot loop {m[3] / tiles:.0f}, general loop {m[9] / tiles:.0f} cyc", flush=True)
+    if m[13] > 0:
+        print(f"    normaliser 0: total {m[13]:.3e} cyc for {m[14]:.0f} candidate tiles ({m[13] / max(m[14], 1):.0f} per tile); "
+              f"TMA thread waited for it {m[12] / m[0]:.1%}", flush=True)
 
 
 if __name__ == "__main__":
