@@ -220,6 +220,8 @@ struct KParams {
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
+    int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
+    uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
     unsigned long long* prof;      // optional [gridDim.x][16] stall-cycle counters (diagnostics)
 };
@@ -251,6 +253,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     uint32_t* norm_count = tmem_slot + 1;                            // kNorm: [2] candidate tiles finished by each normaliser warp
+    uint32_t* cons_count = tmem_slot + 3;                            // kNorm: candidate tiles whose A loads have been issued
     float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
 
     const int warp = threadIdx.x >> 5;
@@ -266,7 +269,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         tma_prefetch_desc(&tmap_cand);
         tma_prefetch_desc(&tmap_ref);
         for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        norm_count[0] = 0; norm_count[1] = 0;
+        norm_count[0] = 0; norm_count[1] = 0; *cons_count = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
         fence_barrier_init();
@@ -306,16 +309,32 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
                         else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
                     }
+                    if (kNorm) red_release_shared_add(cons_count, 1u);
                 }
                 __syncwarp();
                 ++a_it;
+                uint32_t b_in_tile = 0;
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const int32_t rrow0 = rt * kTileN + static_cast<int32_t>(cta_rank * kBRows);
                     for (int kb = 0; kb < p.kb_count; ++kb) {
                         const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1;
                         mbar_wait_timed(&b_empty[bs], bph ^ 1, pr, w_bempty);
+                        if constexpr (kNorm) {
+                            // This tile's fp16 rows were scratch.  A B stage that is free again for the second time since
+                            // the tile began was read by one of this tile's MMAs, which ran only after the A loads had
+                            // landed: the rows have been consumed and nobody reads them again.  Dropping the dirty L2 lines
+                            // now spares (most of) their write-back to HBM.
+                            if (p.discard_a && b_in_tile == static_cast<uint32_t>(p.b_stages) + 1u) {
+                                const int64_t rows_here = min(static_cast<int64_t>(kTileM), p.n_cand - static_cast<int64_t>(row0));
+                                const int64_t bytes = rows_here * p.kb_count * (kBlockK * 2);
+                                const char* base = reinterpret_cast<const char*>(p.cand16) + static_cast<int64_t>(row0) * p.kb_count * (kBlockK * 2);
+                                for (int64_t off = static_cast<int64_t>(lane) * 128; off + 128 <= bytes; off += 32 * 128)
+                                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + off) : "memory");
+                            }
+                            ++b_in_tile;
+                        }
                         if (elect_one()) {
-                            if (leader) mbar_expect_tx(&b_full[bs], kBStageBytes * kCG);
+                            if (leader) mbar_expect_tx(&b_full[bs], p.b_tx_bytes * kCG);
                             uint8_t* dst = smem_b + bs * kBStageBytes;
                             if (kCG == 2) tma_load_2d_cg2(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
                             else          tma_load_2d(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
@@ -414,6 +433,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         uint32_t n_done = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
+            // at most two tiles ahead of the TMA loads: the fp16 rows then stay in L2 until they are consumed (running
+            // free, the warps finished ALL tiles in a third of the kernel and every row made an HBM round trip)
+            while (n_done >= ld_acquire_shared(cons_count) + 2u) __nanosleep(200);
             for (int rb = nw * kR; rb < kTileM; rb += 2 * kR) {
                 if (row0 + rb >= p.n_cand) break;
                 float4 v[kR][4];
@@ -750,7 +772,10 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     const uint32_t smem = a_stages * a_stage + b_stages * b_stage + extra;
 
     CUtensorMap tm_c, tm_r;
-    int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN / cg);
+    // FFR_DIAG_HALF_B=1 (timing experiments only, results are wrong): every B load fetches half its rows -- half the L2 -> SM
+    // traffic with the same MMA work, to tell an L2-bandwidth bound from a latency bound
+    const int half_b = env_int("FFR_DIAG_HALF_B", 0) ? 2 : 1;
+    int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN / cg / half_b);
     if (rc != FFR_OK) return rc;
     rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
     if (rc != FFR_OK) return rc;
@@ -761,6 +786,8 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
     p.acc_stages = env_int("FFR_ACC_STAGES", 2) == 1 ? 1 : 2;
     p.cand32 = cand32; p.cand16 = cand16; p.dim = dim;
+    p.b_tx_bytes = b_stage / half_b;
+    p.discard_a = env_int("FFR_DISCARD_A", 1);
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn = cg == 1 ? (fuse ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)

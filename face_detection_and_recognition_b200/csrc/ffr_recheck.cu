@@ -50,15 +50,11 @@ __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, cons
 // latency and one reduction latency per R references instead of per reference -- the serial form made the few-row
 // rescan pure latency (~1000 cycles per reference).  Same arithmetic per reference as cos_fp32.
 template <int R>
-__device__ __forceinline__ void cos_fp32_multi(const float* __restrict__ c_smem, const float* __restrict__ r0, int n_rows,
-                                               int32_t dim, float cc_sqrt, int lane, bool vec, float (&out)[R]) {
+__device__ __forceinline__ void cos_fp32_ptrs(const float* __restrict__ c_smem, const float* const (&rp)[R], int32_t dim,
+                                              float cc_sqrt, int lane, bool vec, float (&out)[R]) {
     float a[R], b[R];
-    const float* rp[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        a[r] = 0.f; b[r] = 0.f;
-        rp[r] = r0 + static_cast<int64_t>(r < n_rows ? r : n_rows - 1) * dim;
-    }
+    for (int r = 0; r < R; ++r) { a[r] = 0.f; b[r] = 0.f; }
     if (vec) {
         const float4* c4 = reinterpret_cast<const float4*>(c_smem);
         for (int k = lane; k < (dim >> 2); k += 32) {
@@ -90,6 +86,15 @@ __device__ __forceinline__ void cos_fp32_multi(const float* __restrict__ c_smem,
     for (int r = 0; r < R; ++r) out[r] = __fdiv_rn(a[r], __fmul_rn(__fsqrt_rn(b[r]), cc_sqrt));
 }
 
+template <int R>
+__device__ __forceinline__ void cos_fp32_multi(const float* __restrict__ c_smem, const float* __restrict__ r0, int n_rows,
+                                               int32_t dim, float cc_sqrt, int lane, bool vec, float (&out)[R]) {
+    const float* rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) rp[r] = r0 + static_cast<int64_t>(r < n_rows ? r : n_rows - 1) * dim;
+    cos_fp32_ptrs<R>(c_smem, rp, dim, cc_sqrt, lane, vec, out);
+}
+
 __device__ __forceinline__ void emit_result(int32_t row, float best, int32_t bi, float thr, int64_t ref_index_base,
                                             uint8_t* keep, int32_t* best_idx, float* best_val, float band_tol,
                                             int32_t* band_count, int64_t* band_rows, int64_t band_cap) {
@@ -114,26 +119,57 @@ recheck_pairs_phase(float* s_rows, const float* __restrict__ ref, const float* _
     if (count > lists.rec_cap) count = lists.rec_cap;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
-    for (int64_t k = warp; k < count; k += nwarps) {
-        const RecheckRec rec = lists.recs[k];
-        const float* c = cand + static_cast<int64_t>(rec.row) * dim;
+    // The candidate row of the NEXT record is fetched into registers (an HBM miss, ~1.5 us) while the current one is
+    // scored, and the up-to-three references of a record are scored together (one L2 round trip): a warp's rows used to
+    // cost three or four dependent memory latencies each.
+    const bool pipe = vec && dim <= 512;
+    const int nvec = dim >> 2;
+    float4 pre[4];
+    RecheckRec rec{}, rec_next{};
+    int64_t k = warp;
+    auto prefetch = [&](const RecheckRec& r) {
+        const float4* c4 = reinterpret_cast<const float4*>(cand + static_cast<int64_t>(r.row) * dim);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[j] = (lane + 32 * j < nvec) ? __ldg(c4 + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (k < count) { rec = lists.recs[k]; if (pipe) prefetch(rec); }
+    while (k < count) {
         float cc = 0.f;
         __syncwarp();
-        for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+        if (pipe) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (lane + 32 * j < nvec) reinterpret_cast<float4*>(c_smem)[lane + 32 * j] = pre[j];
+                cc = fmaf(pre[j].x, pre[j].x, cc); cc = fmaf(pre[j].y, pre[j].y, cc);
+                cc = fmaf(pre[j].z, pre[j].z, cc); cc = fmaf(pre[j].w, pre[j].w, cc);
+            }
+        } else {
+            const float* c = cand + static_cast<int64_t>(rec.row) * dim;
+            for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+        }
         __syncwarp();
+        const int64_t k_next = k + nwarps;
+        if (k_next < count) { rec_next = lists.recs[k_next]; if (pipe) prefetch(rec_next); }
         const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
-        float best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec);
+        float best;
         int32_t bi = rec.idx1;
-        if (rec.idx2 >= 0) {                                     // the second and third candidate in flight together
-            const float s2 = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx2) * dim, dim, cc_sqrt, lane, vec);
-            const float s3 = rec.idx3 >= 0 ? cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx3) * dim, dim, cc_sqrt, lane, vec)
-                                           : -INFINITY;
-            if (s2 > best || (s2 == best && rec.idx2 < bi)) { best = s2; bi = rec.idx2; }
-            if (rec.idx3 >= 0 && (s3 > best || (s3 == best && rec.idx3 < bi))) { best = s3; bi = rec.idx3; }
+        if (rec.idx2 < 0) {
+            best = cos_fp32(c_smem, ref + static_cast<int64_t>(rec.idx1) * dim, dim, cc_sqrt, lane, vec);
+        } else {
+            const int32_t i3 = rec.idx3 >= 0 ? rec.idx3 : rec.idx2;
+            const float* rp[3] = {ref + static_cast<int64_t>(rec.idx1) * dim, ref + static_cast<int64_t>(rec.idx2) * dim,
+                                  ref + static_cast<int64_t>(i3) * dim};
+            float sc[3];
+            cos_fp32_ptrs<3>(c_smem, rp, dim, cc_sqrt, lane, vec, sc);
+            best = sc[0];
+            if (sc[1] > best || (sc[1] == best && rec.idx2 < bi)) { best = sc[1]; bi = rec.idx2; }
+            if (rec.idx3 >= 0 && (sc[2] > best || (sc[2] == best && rec.idx3 < bi))) { best = sc[2]; bi = rec.idx3; }
         }
         if (lane == 0)
             emit_result(rec.row, best, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
                         band_rows, band_cap);
+        k = k_next;
+        rec = rec_next;
     }
 }
 
@@ -166,7 +202,9 @@ constexpr int kSliceRefs = 1024;
 // last item of a group of kFullGroup rows (full_ctr counts rows x blocks) writes the group's outputs.
 constexpr int kSmallRefs = 32;
 constexpr int kSmallBatch = 8;
-constexpr long long kSmallPairs = 2000000;
+// every flagged row streams the whole reference set once here (no reuse across rows, unlike the tiled walk's 8 rows per
+// reference read): only worth it while that is a few tens of MB of L2 traffic
+constexpr long long kSmallElems = 16000000;
 
 __device__ __forceinline__ void
 rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
@@ -179,39 +217,25 @@ rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, 
     const int64_t n_items = count * nb;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
-    int64_t parked = -1;
-    float cc_sqrt = 0.f;
-    for (int64_t item = warp; item < n_items; item += nwarps) {
-        const int64_t slot = item / nb, blk = item - slot * nb;
-        if (slot != parked) {
-            const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
-            float cc = 0.f;
-            __syncwarp();
-            for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
-            __syncwarp();
-            cc_sqrt = __fsqrt_rn(warp_sum(cc));
-            parked = slot;
-        }
-        const int64_t lo = blk * kSmallRefs;
-        const int64_t hi = (lo + kSmallRefs < n_ref) ? lo + kSmallRefs : n_ref;
-        float best = -INFINITY;
-        int32_t bi = 0x7FFFFFFF;
-        for (int64_t i = lo; i < hi; i += kSmallBatch) {         // ascending + strict '>' = first occurrence
-            float sc[kSmallBatch];
-            const int n_rows = static_cast<int>(hi - i < kSmallBatch ? hi - i : kSmallBatch);
-            cos_fp32_multi<kSmallBatch>(c_smem, ref + i * dim, n_rows, dim, cc_sqrt, lane, vec, sc);
-#pragma unroll
-            for (int r = 0; r < kSmallBatch; ++r)
-                if (r < n_rows && sc[r] > best) { best = sc[r]; bi = static_cast<int32_t>(i + r); }
-        }
-        if (lane == 0 && bi != 0x7FFFFFFF) atomicMax(&lists.full_keys[slot], pack_key(best, bi));
+    // every warp takes a CONTIGUOUS run of items: consecutive reference blocks of the same row, so the row is parked once
+    // and the warp merges its blocks in registers -- one atomicMax + one counter update per (warp, row), not per item
+    const int64_t ipw = (n_items + nwarps - 1) / nwarps;
+    const int64_t i0 = warp * ipw;
+    const int64_t i1 = (i0 + ipw < n_items) ? i0 + ipw : n_items;
+    int64_t cur = -1;
+    int32_t pending = 0;
+    float cc_sqrt = 0.f, best = -INFINITY;
+    int32_t bi = 0x7FFFFFFF;
+    auto flush = [&]() {
+        if (cur < 0 || pending == 0) return;
+        if (lane == 0 && bi != 0x7FFFFFFF) atomicMax(&lists.full_keys[cur], pack_key(best, bi));
         __threadfence();
-        const int64_t g = slot / kFullGroup;
+        const int64_t g = cur / kFullGroup;
         const int64_t rows_in_g = (count - g * kFullGroup < kFullGroup) ? count - g * kFullGroup : kFullGroup;
         int last = 0;
-        if (lane == 0) last = (atomicAdd(&lists.full_ctr[g], 1) == static_cast<int>(rows_in_g * nb) - 1) ? 1 : 0;
+        if (lane == 0) last = (atomicAdd(&lists.full_ctr[g], pending) + pending == static_cast<int>(rows_in_g * nb)) ? 1 : 0;
         last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && lane < rows_in_g) {
+        if (last && lane < rows_in_g) {                          // every block of every row of the group has been merged
             __threadfence();
             const int64_t sl = g * kFullGroup + lane;
             const unsigned long long key = atomicAdd(&lists.full_keys[sl], 0ull);      // coherent read
@@ -222,7 +246,35 @@ rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, 
             emit_result(lists.full_rows[sl], v, bidx, thr, ref_index_base, keep, best_idx, best_val, band_tol,
                         band_count, band_rows, band_cap);
         }
+    };
+    for (int64_t item = i0; item < i1; ++item) {
+        const int64_t slot = item / nb, blk = item - slot * nb;
+        if (slot != cur) {
+            flush();
+            const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
+            float cc = 0.f;
+            __syncwarp();
+            for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+            __syncwarp();
+            cc_sqrt = __fsqrt_rn(warp_sum(cc));
+            cur = slot;
+            pending = 0;
+            best = -INFINITY;
+            bi = 0x7FFFFFFF;
+        }
+        const int64_t lo = blk * kSmallRefs;
+        const int64_t hi = (lo + kSmallRefs < n_ref) ? lo + kSmallRefs : n_ref;
+        for (int64_t i = lo; i < hi; i += kSmallBatch) {         // ascending + strict '>' = first occurrence
+            float sc[kSmallBatch];
+            const int n_rows = static_cast<int>(hi - i < kSmallBatch ? hi - i : kSmallBatch);
+            cos_fp32_multi<kSmallBatch>(c_smem, ref + i * dim, n_rows, dim, cc_sqrt, lane, vec, sc);
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r)
+                if (r < n_rows && sc[r] > best) { best = sc[r]; bi = static_cast<int32_t>(i + r); }
+        }
+        ++pending;
     }
+    flush();
 }
 
 // One launch re-checks everything K2 flagged: phase A = K3a (pairs list), phase B = K3b (full-rescan list; small or
@@ -243,7 +295,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
     if (count == 0) return;
-    if (static_cast<long long>(count) * n_ref <= kSmallPairs) {
+    if (static_cast<long long>(count) * n_ref * dim <= kSmallElems) {
         rescan_small_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, count, band_tol,
                            band_count, band_rows, band_cap, kVec);
         return;
