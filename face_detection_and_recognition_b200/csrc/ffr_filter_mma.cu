@@ -41,11 +41,11 @@ namespace ffr {
 namespace {
 
 constexpr int kTileM = 128;          // candidates per CTA tile (TMEM lanes)
-constexpr int kTileN = 256;          // references per accumulator stage (TMEM columns)
+constexpr int kTileN = 256;          // references per accumulator stage (TMEM columns), A-from-shared-memory variant
 constexpr int kBlockK = 64;          // fp16 per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxAStages = 4;
-constexpr int kMaxBStages = 12;
+constexpr int kMaxBStages = 16;
 constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-block of the A tile
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;                       // 227 KiB opt-in maximum
@@ -181,6 +181,30 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {         // arri
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
         ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
 }
+// ---- A operand in tensor memory ("TS" form): D[tmem] (+)= A[tmem] * B[smem desc]^T ----------------------------
+// A tile layout in TMEM: lane = candidate row, one 32-bit column holds two consecutive K elements, so a K = 16 MMA step
+// reads 8 columns.  tcgen05.cp .128x256b copies exactly such a slice (128 rows x 32 bytes) out of the K-major
+// SWIZZLE_128B staging tile, described by the same matrix descriptor the SS-form MMA would have used for A.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc, bool cg2) {
+    if (cg2) asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+    else     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate, bool cg2) {
+    if (cg2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -220,6 +244,9 @@ struct KParams {
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
+    int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
+    int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
+    int decouple_a;                // producer: A loads issued opportunistically while the B stream runs (FFR_DECOUPLE_A, default on)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
@@ -232,13 +259,15 @@ struct KParams {
 // and write the fp16 rows into the workspace, while the tensor core works on the current tile; the TMA producer waits
 // for a per-CTA counter before it loads a tile.  The rows come back through L2, HBM sees the fp32 embeddings once, and
 // the 0.6 ms K1 pass over 1.25 M x 512 disappears behind the MMAs (the kernel needs < 10 % of K1's bandwidth).
-template <int kCG, int kEW, bool kNorm>
+template <int kCG, int kEW, bool kNorm, int kAccN>
 __global__ void __launch_bounds__(64 + 32 * kEW + (kNorm ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const KParams p) {
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
-    constexpr int kChunksPerPart = (kTileN / 32) / kParts;
-    constexpr uint32_t kBRows = kTileN / kCG;                       // B rows this CTA loads per K-block
+    constexpr bool kTS = kAccN != kTileN;                           // A operand in tensor memory (kAccN 192 | 128), else shared memory
+    constexpr int kChunksPerPart = (kAccN / 32) / kParts;
+    constexpr uint32_t kBRows = kAccN / kCG;                        // B rows this CTA loads per K-block
+    constexpr uint32_t kATmemCol = 2 * kAccN;                       // kTS: first TMEM column of the A tile (after both accumulator stages)
     constexpr uint32_t kBStageBytes = kBRows * kBlockK * 2;         // 32 KiB (kCG 1) / 16 KiB (kCG 2)
     extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t a_stage_bytes = static_cast<uint32_t>(p.kb_count) * kABlockBytes;
@@ -262,7 +291,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     const bool leader = cta_rank == 0;
     const int64_t n_tiles = (p.n_cand + kTileM * kCG - 1) / (kTileM * kCG);   // tiles of the CTA pair
     const int64_t tile0 = blockIdx.x / kCG, tile_stride = gridDim.x / kCG;
-    const int32_t n_rt = static_cast<int32_t>((p.n_ref + kTileN - 1) / kTileN);
+    const int32_t n_rt = static_cast<int32_t>((p.n_ref + kAccN - 1) / kAccN);
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -284,25 +313,25 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Keeping the warp
-        // converged matters: UTMALDG / UTCHMMA are uniform-datapath instructions and inside a divergent region
-        // ptxas wraps each of them in a serialising vote loop (~200 cycles per MMA issue, measured).
-        {
-            uint32_t a_it = 0, b_it = 0;
+        // ===================== TMA producer: ONE elected thread runs the whole loop =====================
+        // (Inside `if (elect_one())` ptxas knows a single lane is active and emits plain UTMALDG / UTCHMMA; under
+        // `if (lane == 0)` it wrapped each of them in a serialising vote loop, ~200 cycles per instruction.)  Ring
+        // positions and phases are carried incrementally: a runtime `% stages` per K-block is a 25-instruction
+        // division with MUFU latency on the critical path of every stage.
+        if (elect_one()) {
             const bool pr = p.prof != nullptr;
-            unsigned long long w_aempty = 0, w_bempty = 0, w_norm = 0;
+            unsigned long long w_aempty = 0, w_bempty = 0;
             const long long t_begin = clock64();
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, a_it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-                const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
                 const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
-                if constexpr (kNorm) {                      // this tile's fp16 rows must have been written (both warps)
-                    const long long tn0 = pr ? clock64() : 0;
-                    while (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it) { }
-                    if (pr) w_norm += static_cast<unsigned long long>(clock64() - tn0);
-                }
-                mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_aempty);
-                if (elect_one()) {
+                // The B stream does not depend on the candidate tile: it keeps flowing across tile boundaries, and this
+                // tile's A loads go out the moment their stage is free (and, kNorm, the fp16 rows are written) -- probed
+                // without blocking while the thread waits for B slots.
+                bool need_a = true;
+                auto try_issue_a = [&]() {
+                    if (kNorm && (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
+                    if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return;
                     if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
                     for (int kb = 0; kb < p.kb_count; ++kb) {
                         uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
@@ -310,15 +339,21 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
                     }
                     if (kNorm) red_release_shared_add(cons_count, 1u);
-                }
-                __syncwarp();
-                ++a_it;
+                    need_a = false;
+                };
+                try_issue_a();
+                if (!p.decouple_a) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
                 uint32_t b_in_tile = 0;
                 for (int rt = 0; rt < n_rt; ++rt) {
-                    const int32_t rrow0 = rt * kTileN + static_cast<int32_t>(cta_rank * kBRows);
+                    const int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
                     for (int kb = 0; kb < p.kb_count; ++kb) {
-                        const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1;
-                        mbar_wait_timed(&b_empty[bs], bph ^ 1, pr, w_bempty);
+                        if (need_a) {
+                            const long long tw0 = pr ? clock64() : 0;
+                            while (!mbar_test_wait(&b_empty[bs], bph ^ 1)) { if (need_a) try_issue_a(); }
+                            if (pr) w_bempty += static_cast<unsigned long long>(clock64() - tw0);
+                        } else {
+                            mbar_wait_timed(&b_empty[bs], bph ^ 1, pr, w_bempty);
+                        }
                         if constexpr (kNorm) {
                             // This tile's fp16 rows were scratch.  A B stage that is free again for the second time since
                             // the tile began was read by one of this tile's MMAs, which ran only after the A loads had
@@ -328,88 +363,102 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                                 const int64_t rows_here = min(static_cast<int64_t>(kTileM), p.n_cand - static_cast<int64_t>(row0));
                                 const int64_t bytes = rows_here * p.kb_count * (kBlockK * 2);
                                 const char* base = reinterpret_cast<const char*>(p.cand16) + static_cast<int64_t>(row0) * p.kb_count * (kBlockK * 2);
-                                for (int64_t off = static_cast<int64_t>(lane) * 128; off + 128 <= bytes; off += 32 * 128)
+                                for (int64_t off = 0; off + 128 <= bytes; off += 128)
                                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + off) : "memory");
                             }
                             ++b_in_tile;
                         }
-                        if (elect_one()) {
-                            if (leader) mbar_expect_tx(&b_full[bs], p.b_tx_bytes * kCG);
-                            uint8_t* dst = smem_b + bs * kBStageBytes;
-                            if (kCG == 2) tma_load_2d_cg2(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
-                            else          tma_load_2d(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
-                        }
-                        __syncwarp();
-                        ++b_it;
+                        if (leader) mbar_expect_tx(&b_full[bs], p.b_tx_bytes * kCG);
+                        uint8_t* dst = smem_b + bs * kBStageBytes;
+                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
+                        else          tma_load_2d(dst, &tmap_ref, &b_full[bs], kb * kBlockK, rrow0, kEvictLast);
+                        if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
                 }
+                if (need_a) {                               // fewer B loads than ring slots: nothing made the thread wait
+                    const long long tw0 = pr ? clock64() : 0;
+                    while (need_a) try_issue_a();
+                    if (pr) w_aempty += static_cast<unsigned long long>(clock64() - tw0);
+                }
+                ++a_it;
+                if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
-            if (pr && lane == 0) {
+            if (pr) {
                 p.prof[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
                 p.prof[blockIdx.x * 16 + 1] = w_aempty;
                 p.prof[blockIdx.x * 16 + 2] = w_bempty;
-                p.prof[blockIdx.x * 16 + 12] = w_norm;
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA; whole warp converged, one elected lane issues) ==========
-        if (leader) {
-            uint32_t a_it = 0, b_it = 0, t_it = 0;
+        // ===================== MMA issuer: one elected thread of the leader CTA =====================
+        if (leader && elect_one()) {
             const bool pr = p.prof != nullptr;
             unsigned long long w_afull = 0, w_tempty = 0, w_bfull = 0;
             const long long t_begin = clock64();
             // UMMA smem descriptor, K-major SWIZZLE_128B: hi word is constant (SBO 1024 B, version 1, layout 2);
             // lo word = (address >> 4) | LBO(1) << 16, advanced by 2 (32 bytes) per K = 16 step.
             constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint64_t kDescHi64 = static_cast<uint64_t>(kDescHi) << 32;
+            constexpr int kSteps = kBlockK / kUmmaK;                        // MMAs per K-block
+            const uint32_t b_lo_base = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t idesc_full = umma_idesc_f16(kTileM * kCG, kAccN);
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, tph = 0, t_it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-                const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1;
                 mbar_wait_timed(&a_full[as], aph, pr, w_afull);
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                if constexpr (kTS) {
+                    // staging tile -> tensor memory, one 128 x 32-byte slice per K = 16 step.  tcgen05.cp and tcgen05.mma
+                    // execute in issue order, so these copies queue behind the previous tile's MMAs (which still read the
+                    // old A columns) and ahead of this tile's; the commit hands the staging tile back to the TMA producer
+                    // as soon as the copies have read it -- the next tile's A loads overlap this tile's MMAs.
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < kSteps; ++k)
+                            tmem_cp_128x256b(tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u,
+                                             kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k), kCG == 2);
+                    }
+                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);
+                }
                 for (int rt = 0; rt < n_rt; ++rt) {
-                    const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
-                    const uint32_t tph = p.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
-                    uint32_t n_mma = kTileN;
-                    if (kCG == 1) {                             // tail reference tile: only as many columns as needed
-                        int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kTileN;
-                        if (ncols < kTileN) n_mma = static_cast<uint32_t>((ncols + 15) & ~int64_t(15));
+                    uint32_t idesc = idesc_full;
+                    if (kCG == 1 && !kTS) {                     // tail reference tile: only as many columns as needed
+                        const int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kAccN;
+                        if (ncols < kAccN) idesc = umma_idesc_f16(kTileM * kCG, static_cast<uint32_t>((ncols + 15) & ~int64_t(15)));
                     }
-                    const uint32_t idesc = umma_idesc_f16(kTileM * kCG, n_mma);
-                    const uint32_t d_tmem = tmem_base + acc * kTileN;
+                    const uint32_t d_tmem = tmem_base + acc * kAccN;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
-                        const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1;
                         mbar_wait_timed(&b_full[bs], bph, pr, w_bfull);
                         tc_fence_after();
-                        const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
-                        const uint32_t b_lo = ((smem_u32(smem_b + bs * kBStageBytes) & 0x3FFFFu) >> 4) | (1u << 16);
-                        if (elect_one()) {
+                        const uint32_t b_lo = b_lo_base + bs * (kBStageBytes >> 4);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                                const uint64_t da = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2u * k);
-                                const uint64_t db = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2u * k);
-                                if (kCG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                                else          umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kSteps; ++k) {
+                            const uint64_t db = kDescHi64 | (b_lo + 2u * k);
+                            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                            if constexpr (kTS) {
+                                umma_f16_ts(d_tmem, tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u, db, idesc, accum, kCG == 2);
+                            } else {
+                                const uint64_t da = kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k);
+                                if (kCG == 2) umma_f16_cg2(d_tmem, da, db, idesc, accum);
+                                else          umma_f16(d_tmem, da, db, idesc, accum);
                             }
-                            if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
                         }
-                        __syncwarp();
-                        ++b_it;
+                        if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
+                        if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
-                    if (elect_one()) {
-                        if (kCG == 2) umma_commit_cg2(&t_full[acc]); else umma_commit(&t_full[acc]);   // accumulator ready
-                    }
-                    __syncwarp();
+                    if (kCG == 2) umma_commit_cg2(&t_full[acc]); else umma_commit(&t_full[acc]);       // accumulator ready
+                    if (p.acc_stages == 2) { acc ^= 1u; if (acc == 0u) tph ^= 1u; } else { tph ^= 1u; }
                     ++t_it;
                 }
-                if (elect_one()) {
+                if constexpr (!kTS) {
                     if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);       // A stage reusable
                 }
-                __syncwarp();
-                ++a_it;
+                if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
-            if (pr && lane == 0) {
+            if (pr) {
                 p.prof[blockIdx.x * 16 + 4] = static_cast<unsigned long long>(clock64() - t_begin);
                 p.prof[blockIdx.x * 16 + 5] = w_afull;
                 p.prof[blockIdx.x * 16 + 6] = w_tempty;
@@ -417,6 +466,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 p.prof[blockIdx.x * 16 + 8] = t_it;
             }
         }
+        __syncwarp();
     } else if (kNorm && warp >= 2 + kEW) {
         // ===================== normaliser warps: fp32 rows -> L2-normalised fp16 rows in the workspace (K1 in-kernel) ====
         // Warp nw of 2 owns rows nw*4 .. nw*4+3 of every group of 8 rows of the CTA's tile; one row at a time per lane
@@ -435,7 +485,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
             // at most two tiles ahead of the TMA loads: the fp16 rows then stay in L2 until they are consumed (running
             // free, the warps finished ALL tiles in a third of the kernel and every row made an HBM round trip)
-            while (n_done >= ld_acquire_shared(cons_count) + 2u) __nanosleep(200);
+            while (n_done >= ld_acquire_shared(cons_count) + static_cast<uint32_t>(p.norm_ahead)) __nanosleep(200);
             for (int rb = nw * kR; rb < kTileM; rb += 2 * kR) {
                 if (row0 + rb >= p.n_cand) break;
                 float4 v[kR][4];
@@ -447,7 +497,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int f = lane + 32 * j;
-                        v[u][j] = (f < nvec) ? ldg_stream_f4(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[u][j] = (f < nvec) ? (p.norm_evict_first ? ldg_stream_evict_first_f4(src + f) : ldg_stream_f4(src + f))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
@@ -517,9 +568,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mbar_wait_timed(&t_full[acc], tph, pr, w_tfull);
                 const long long tp0 = pr ? clock64() : 0;
                 tc_fence_after();
-                const int32_t col0 = rt * kTileN;
+                const int32_t col0 = rt * kAccN;
                 const int64_t ncols64 = p.n_ref - static_cast<int64_t>(col0);
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + h * (kChunksPerPart * 32);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccN + h * (kChunksPerPart * 32);
                 const int32_t base0 = col0 + h * (kChunksPerPart * 32);
                 if (hot_ok) {
                     // ---- hot loop: straight-line code.  All of this warp's columns are
@@ -539,7 +590,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (kCG == 2 && !leader) mbar_arrive_leader_relaxed(&t_empty[acc]);
                         else                     mbar_arrive(&t_empty[acc]);
                     }
-                    if (ncols64 < kTileN) {                        // partial last reference tile: columns >= n_ref -> -inf
+                    if (ncols64 < kAccN) {                         // partial last reference tile: columns >= n_ref -> -inf
                         const int n_left = static_cast<int>(ncols64) - h * (kChunksPerPart * 32);
 #pragma unroll
                         for (int cc = 0; cc < kChunksPerPart; ++cc)
@@ -559,7 +610,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
                     // ---- general loop, one chunk at a time: diagnostics only (score dump, epilogue modes)
-                    const int ncols = ncols64 > kTileN ? kTileN : static_cast<int>(ncols64);
+                    const int ncols = ncols64 > kAccN ? kAccN : static_cast<int>(ncols64);
                     const int n_left = ncols - h * (kChunksPerPart * 32);             // live columns of this warp's part
                     float va[32];
                     for (int cc = 0; cc < kChunksPerPart && cc * 32 < n_left; ++cc) {
@@ -755,9 +806,17 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (cg != 2 || (sms & 1)) cg = 1;
     const bool fuse = cand32 != nullptr;
     const int kb = dim_pad / kBlockK;
+    // A operand in tensor memory (cta_group::2 only, FFR_A_TMEM=1): the A tile leaves shared memory for 32 TMEM columns per
+    // K-block (tcgen05.cp from a single staging tile), the accumulator stages shrink to 192 (dim <= 256) or 128 columns and
+    // the B ring gets the rest of shared memory.  Correct (same tests), but measured SLOWER than the SS form on B200: an
+    // N = 128 / 192 MMA with A in TMEM costs ~108 / ~144 cycles against 64 / 96 ideal, while the SS form's N = 256 MMA runs
+    // at ~141 of 128 -- per 256 reference columns 6898 vs 4526 cycles at dim 512, 1539 vs 1374 at dim 128.  Off by default.
+    int acc_n = kTileN;
+    if (cg == 2 && env_int("FFR_A_TMEM", 0) != 0) acc_n = dim_pad <= 256 ? 192 : 128;
+    const bool ts = acc_n != kTileN;
     const uint32_t a_stage = kb * kABlockBytes;
-    const uint32_t b_stage = (kTileN / cg) * kBlockK * 2;
-    int a_stages = env_int("FFR_A_STAGES", a_stage_count(dim_pad));
+    const uint32_t b_stage = (acc_n / cg) * kBlockK * 2;
+    int a_stages = ts ? 1 : env_int("FFR_A_STAGES", a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
     const int ew = 8;      // 16 epilogue warps were measured: no gain
@@ -775,7 +834,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     // FFR_DIAG_HALF_B=1 (timing experiments only, results are wrong): every B load fetches half its rows -- half the L2 -> SM
     // traffic with the same MMA work, to tell an L2-bandwidth bound from a latency bound
     const int half_b = env_int("FFR_DIAG_HALF_B", 0) ? 2 : 1;
-    int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, kTileN / cg / half_b);
+    int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, acc_n / cg / half_b);
     if (rc != FFR_OK) return rc;
     rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
     if (rc != FFR_OK) return rc;
@@ -788,16 +847,23 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.cand32 = cand32; p.cand16 = cand16; p.dim = dim;
     p.b_tx_bytes = b_stage / half_b;
     p.discard_a = env_int("FFR_DISCARD_A", 1);
+    p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
+    p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
+    p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
+    if (p.norm_ahead < 1) p.norm_ahead = 1;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-    KernelFn fn = cg == 1 ? (fuse ? filter_mma_kernel<1, 8, true> : filter_mma_kernel<1, 8, false>)
-                          : (fuse ? filter_mma_kernel<2, 8, true> : filter_mma_kernel<2, 8, false>);
+    KernelFn fn;
+    if (cg == 1)           fn = fuse ? filter_mma_kernel<1, 8, true, 256> : filter_mma_kernel<1, 8, false, 256>;
+    else if (acc_n == 256) fn = fuse ? filter_mma_kernel<2, 8, true, 256> : filter_mma_kernel<2, 8, false, 256>;
+    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, true, 192> : filter_mma_kernel<2, 8, false, 192>;
+    else                   fn = fuse ? filter_mma_kernel<2, 8, true, 128> : filter_mma_kernel<2, 8, false, 128>;
     static bool attr_set = false;
     if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        FFR_CUDA_TRY(cudaFuncSetAttribute(filter_mma_kernel<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        KernelFn all[] = {filter_mma_kernel<1, 8, true, 256>, filter_mma_kernel<1, 8, false, 256>, filter_mma_kernel<2, 8, true, 256>,
+                          filter_mma_kernel<2, 8, false, 256>, filter_mma_kernel<2, 8, true, 192>, filter_mma_kernel<2, 8, false, 192>,
+                          filter_mma_kernel<2, 8, true, 128>, filter_mma_kernel<2, 8, false, 128>};
+        for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);

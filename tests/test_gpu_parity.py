@@ -294,3 +294,12 @@ def test_errors_are_loud(ffr_lib, ops):
         idx = torch.empty(32, dtype=torch.int32, device="cuda")
         check(ffr_lib.ffr_filter(ref.data_ptr(), 16, cand.data_ptr(), 32, 128, 0, None, None, 0, 0.5, 0,
                                  keep.data_ptr(), idx.data_ptr(), None, None, 0, None))
+
+
+@pytest.mark.parametrize("n_ref,n_cand,dim", [(700, 3000, 128), (513, 2500, 256), (1000, 2049, 512), (300, 40_000, 384)])
+def test_a_operand_in_tensor_memory_variant(ops, monkeypatch, n_ref, n_cand, dim):
+    """K2 with the A tile in tensor memory (tcgen05.cp from a staging tile, tcgen05.mma with a TMEM A operand, 192- or
+    128-column accumulator stages; FFR_A_TMEM=1, off by default because it measured slower): same parity bar."""
+    monkeypatch.setenv("FFR_A_TMEM", "1")
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=3 * dim + n_ref, n_adversarial=100, n_dup_refs=8)
+    _check_cosine(ops, ref, cand, 0.5)
