@@ -244,6 +244,7 @@ struct KParams {
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
+    int norm_diag;                 // kNorm diagnostics (timing only, wrong results): 1 = no loads, 2 = no stores (FFR_NORM_DIAG)
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
     int decouple_a;                // producer: A loads issued opportunistically while the B stream runs (FFR_DECOUPLE_A, default on)
@@ -343,7 +344,6 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 };
                 try_issue_a();
                 if (!p.decouple_a) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
-                uint32_t b_in_tile = 0;
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
                     for (int kb = 0; kb < p.kb_count; ++kb) {
@@ -353,20 +353,6 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             if (pr) w_bempty += static_cast<unsigned long long>(clock64() - tw0);
                         } else {
                             mbar_wait_timed(&b_empty[bs], bph ^ 1, pr, w_bempty);
-                        }
-                        if constexpr (kNorm) {
-                            // This tile's fp16 rows were scratch.  A B stage that is free again for the second time since
-                            // the tile began was read by one of this tile's MMAs, which ran only after the A loads had
-                            // landed: the rows have been consumed and nobody reads them again.  Dropping the dirty L2 lines
-                            // now spares (most of) their write-back to HBM.
-                            if (p.discard_a && b_in_tile == static_cast<uint32_t>(p.b_stages) + 1u) {
-                                const int64_t rows_here = min(static_cast<int64_t>(kTileM), p.n_cand - static_cast<int64_t>(row0));
-                                const int64_t bytes = rows_here * p.kb_count * (kBlockK * 2);
-                                const char* base = reinterpret_cast<const char*>(p.cand16) + static_cast<int64_t>(row0) * p.kb_count * (kBlockK * 2);
-                                for (int64_t off = 0; off + 128 <= bytes; off += 128)
-                                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + off) : "memory");
-                            }
-                            ++b_in_tile;
                         }
                         if (leader) mbar_expect_tx(&b_full[bs], p.b_tx_bytes * kCG);
                         uint8_t* dst = smem_b + bs * kBStageBytes;
@@ -486,6 +472,19 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // at most two tiles ahead of the TMA loads: the fp16 rows then stay in L2 until they are consumed (running
             // free, the warps finished ALL tiles in a third of the kernel and every row made an HBM round trip)
             while (n_done >= ld_acquire_shared(cons_count) + static_cast<uint32_t>(p.norm_ahead)) __nanosleep(200);
+            // The fp16 rows are scratch: once a tile has been consumed nobody reads them again, and dropping the dirty L2
+            // lines spares their write-back to HBM.  Passing the wait above means the A loads of tile n_done - 2 (or later)
+            // have been issued, which needs that tile's A stage free, i.e. every MMA of tile n_done - 2 - a_stages retired --
+            // and with them that tile's A loads.  (Done here, not by the TMA thread: 1024 discards per tile in the one
+            // thread that feeds the B ring cost 7 % of the kernel.)
+            if (p.discard_a && n_done >= 2u + static_cast<uint32_t>(p.a_stages)) {
+                const int64_t old_tile = tile - static_cast<int64_t>(2 + p.a_stages) * tile_stride;
+                const int64_t old_row0 = old_tile * (kTileM * kCG) + cta_rank * kTileM;
+                const int64_t bytes = static_cast<int64_t>(kTileM) * ld16 * 2;          // a full tile: it is not the last one
+                const char* base = reinterpret_cast<const char*>(p.cand16) + old_row0 * ld16 * 2;
+                for (int64_t off = static_cast<int64_t>(nw * 32 + lane) * 128; off + 128 <= bytes; off += 64 * 128)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + off) : "memory");
+            }
             for (int rb = nw * kR; rb < kTileM; rb += 2 * kR) {
                 if (row0 + rb >= p.n_cand) break;
                 float4 v[kR][4];
@@ -497,8 +496,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int f = lane + 32 * j;
-                        v[u][j] = (f < nvec) ? (p.norm_evict_first ? ldg_stream_evict_first_f4(src + f) : ldg_stream_f4(src + f))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[u][j] = (f < nvec && !(p.norm_diag & 1)) ? (p.norm_evict_first ? ldg_stream_evict_first_f4(src + f) : ldg_stream_f4(src + f))
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
@@ -527,7 +526,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                                     pk.x = *reinterpret_cast<const uint32_t*>(&h0);
                                     pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                                 }
-                                reinterpret_cast<uint2*>(dst)[f] = pk;
+                                if (!(p.norm_diag & 2)) reinterpret_cast<uint2*>(dst)[f] = pk;
                             }
                         }
                     }
@@ -849,6 +848,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.discard_a = env_int("FFR_DISCARD_A", 1);
     p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
+    p.norm_diag = env_int("FFR_NORM_DIAG", 0);
     p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 
