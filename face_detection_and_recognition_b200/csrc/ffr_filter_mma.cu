@@ -818,7 +818,9 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     int a_stages = ts ? 1 : env_int("FFR_A_STAGES", a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
-    const int ew = 8;      // 16 epilogue warps were measured: no gain
+    // epilogue warps: 8 = 4 TMEM lane quadrants x 2 column parts.  FFR_EPI_WARPS=16 (SS form, cta_group::2 only) splits the
+    // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
+    const int ew = (cg == 2 && env_int("FFR_EPI_WARPS", 8) == 16 && env_int("FFR_A_TMEM", 0) == 0) ? 16 : 8;
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     const uint32_t budget = kSmemLimit - extra;
     while (a_stages > 1 && a_stages * a_stage + 2 * b_stage > budget) --a_stages;
@@ -854,7 +856,8 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn;
-    if (cg == 1)           fn = fuse ? filter_mma_kernel<1, 8, true, 256> : filter_mma_kernel<1, 8, false, 256>;
+    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, true, 256> : filter_mma_kernel<2, 16, false, 256>;
+    else if (cg == 1)      fn = fuse ? filter_mma_kernel<1, 8, true, 256> : filter_mma_kernel<1, 8, false, 256>;
     else if (acc_n == 256) fn = fuse ? filter_mma_kernel<2, 8, true, 256> : filter_mma_kernel<2, 8, false, 256>;
     else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, true, 192> : filter_mma_kernel<2, 8, false, 192>;
     else                   fn = fuse ? filter_mma_kernel<2, 8, true, 128> : filter_mma_kernel<2, 8, false, 128>;
@@ -862,7 +865,8 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (!attr_set) {
         KernelFn all[] = {filter_mma_kernel<1, 8, true, 256>, filter_mma_kernel<1, 8, false, 256>, filter_mma_kernel<2, 8, true, 256>,
                           filter_mma_kernel<2, 8, false, 256>, filter_mma_kernel<2, 8, true, 192>, filter_mma_kernel<2, 8, false, 192>,
-                          filter_mma_kernel<2, 8, true, 128>, filter_mma_kernel<2, 8, false, 128>};
+                          filter_mma_kernel<2, 8, true, 128>, filter_mma_kernel<2, 8, false, 128>,
+                          filter_mma_kernel<2, 16, true, 256>, filter_mma_kernel<2, 16, false, 256>};
         for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
