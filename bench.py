@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic embeddings that are already resident in HBM:
-K1 (row L2-normalise + fp16 cast of candidates and references) -> K2 (tcgen05 cosine GEMM fused with threshold and
-running max/argmax) -> K3 (fp32 re-check of near-tie / near-threshold rows) [-> K4 one NCCL allgather of the packed
+K1 (row L2-normalise + fp16 cast of the references; of the candidates too unless K2 does it in-kernel) -> K2 (tcgen05
+cosine GEMM fused with the candidates' normalisation, the threshold and the running max/argmax) -> K3 (fp32 re-check
+of near-tie / near-threshold rows) [-> K4 one NCCL allgather of the packed
 {best_idx, keep} when N > 1].  Prints ONE JSON line (rank 0).  See DESIGN.md §6 for how every field is derived.
 
 Workloads (BASELINE.json configs): the default, cfg3, is the per-GPU shard of configs[3] (10k references x 10M
@@ -112,6 +113,9 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        deadline = time.perf_counter() + 1.5                 # very short timed regions: wait for at least one sample
+        while not self.rows and time.perf_counter() < deadline:
+            time.sleep(0.02)
         time.sleep(0.06)
         self.proc.terminate()
         inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.05] or [r for (_, r) in self.rows[-3:]]

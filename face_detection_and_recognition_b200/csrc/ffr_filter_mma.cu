@@ -17,20 +17,20 @@
 //   * candidates -> MMA M (TMEM lanes), references -> MMA N (TMEM columns).  A CTA keeps its 128-candidate
 //     A tile (all of K) resident in shared memory and streams 256-reference B tiles, K-block by K-block,
 //     out of L2 through a TMA/mbarrier ring: per 128 x 256 x K tile only B moves.
-//   * kCG == 2: two CTAs of a cluster (an SM pair) share every B tile -- each loads half of it and one
+//   * kCG == 2 (default): two CTAs of a cluster (an SM pair) share every B tile -- each loads half of it and one
 //     tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA reads A and B from both CTAs' shared memory
-//     and writes 128 accumulator rows into each CTA's TMEM.  Half the B bytes per SM from L2, and a ring that
-//     is twice as deep in time for the same shared memory.
-//   * warp 0: TMA producer.  warp 1: tcgen05.mma issuer (single thread, leader CTA) + TMEM owner.
-//     warps 2-9: epilogue, one thread per (candidate row, column half): the max/argmax over references is a
-//     pure in-register reduction over TMEM columns -- no shuffles; the two column halves of a row are merged
-//     through 2.5 KB of shared memory once per candidate tile.
+//     and writes 128 accumulator rows into each CTA's TMEM.
+//   * warp 0: TMA producer, warp 1: tcgen05.mma issuer + TMEM owner -- one elected thread each, ring positions and
+//     phases carried incrementally.  warps 2-9: epilogue, one thread per (candidate row, column half): the
+//     max/argmax over references is a pure in-register reduction over TMEM columns -- no shuffles; the two column
+//     halves of a row are merged through shared memory once per candidate tile.  kNorm: warps 10-11 L2-normalise
+//     the fp32 rows of the CTA's next candidate tile into the fp16 workspace (K1 inside K2).
 //   * the accumulator is double buffered in TMEM (2 x 256 of the 512 columns): the MMAs of reference tile
 //     t+1 overlap the epilogue of tile t.
-//   * epilogue per 32-column chunk: tcgen05.ld -> max tree (3-input max) -> only if the chunk max comes
-//     within delta of the running best is the chunk rescanned (8 columns at a time) to update the running
-//     top-3 {best, idx} {second, idx} third.  Ascending column order + strict '>' = np.argmax first
-//     occurrence.  The top-3 is what K3 needs to make the index and keep bit exact in fp32.
+//   * epilogue per reference tile: four tcgen05.ld in flight -> stage released -> four 3-input-max trees -> one
+//     branch on the tile maximum -> (rarely) update_chunk.  Ascending column order + strict '>' = np.argmax first
+//     occurrence.  The running top-4 (+ the "hidden column" level amb) is what K3 needs to make the index and keep
+//     bit exact in fp32.
 #include <cuda.h>
 #include <stdlib.h>
 
