@@ -119,6 +119,48 @@ __device__ __forceinline__ void update_chunk(const float (&v)[32], float cmax, i
     gate = t.b1 - delta;
 }
 
+// Batched form of the update path for SHORT reference sets, where nearly every chunk of every tile reaches the gate in
+// some lane (a warp pays for the union of its lanes' record-setting chunks: with 1000 references that is all of them) and
+// the sequential form is a chain of dependent ~110-instruction blocks at IPC 0.3.  All kC chunks of the part are masked
+// against ONE floor w0 = max(best, part maximum) - delta: a column below w0 is outside the window once this part has been
+// seen, so nothing that could matter later is skipped, and the kC mask builds are independent instruction streams.
+template <int kC>
+__device__ __forceinline__ void update_part(const float (&v)[kC][32], const float (&cm)[kC], float m, int32_t base0, float delta,
+                                            Top3& t, float& gate, float& amb) {
+    const float w0 = fmaxf(t.b1, m) - delta;
+    uint32_t ge[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+        uint32_t g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g[k] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k] |= (v[c][8 * k + j] >= w0) ? (1u << (8 * k + j)) : 0u;
+        }
+        ge[c] = (g[0] | g[1]) | (g[2] | g[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+        if (ge[c] != 0) {
+            uint32_t pos = ge[c];
+            if (pos & (pos - 1)) {                                // several columns of this chunk inside the window (rare)
+                amb = fmaxf(amb, cm[c]);
+                uint32_t g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    g[k] = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[k] |= (v[c][8 * k + j] == cm[c]) ? (1u << (8 * k + j)) : 0u;
+                }
+                pos = (g[0] | g[1]) | (g[2] | g[3]);
+            }
+            if (pos != 0) top3_insert(t, cm[c], base0 + c * 32 + __ffs(pos) - 1);
+        }
+    }
+    gate = t.b1 - delta;
+}
+
 __device__ __forceinline__ float chunk_max(const float (&v)[32]) {
     float s[4];
 #pragma unroll
@@ -244,6 +286,7 @@ struct KParams {
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
+    int batch_updates;             // epilogue: batched update path (n_ref <= FFR_BATCH_UPDATE_REFS, default 8192)
     int norm_diag;                 // kNorm diagnostics (timing only, wrong results): 1 = no loads, 2 = no stores (FFR_NORM_DIAG)
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
@@ -552,6 +595,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
         const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
+        const bool batch_updates = p.batch_updates != 0;         // short reference sets: see update_part
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -602,9 +646,13 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                     for (int cc = 1; cc < kChunksPerPart; ++cc) m = fmaxf(m, cm[cc]);
                     if (m >= gate) {
+                        if (batch_updates) {
+                            update_part<kChunksPerPart>(v, cm, m, base0, p.delta, t, gate, amb);
+                        } else {
 #pragma unroll
-                        for (int cc = 0; cc < kChunksPerPart; ++cc)
-                            if (cm[cc] >= gate) update_chunk(v[cc], cm[cc], base0 + cc * 32, p.delta, t, gate, amb);
+                            for (int cc = 0; cc < kChunksPerPart; ++cc)
+                                if (cm[cc] >= gate) update_chunk(v[cc], cm[cc], base0 + cc * 32, p.delta, t, gate, amb);
+                        }
                     }
                     if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
@@ -851,6 +899,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
     p.norm_diag = env_int("FFR_NORM_DIAG", 0);
+    p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;
     p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 

@@ -11,6 +11,8 @@
 // is reduced with warp shuffles, and each lane normalises and stores what it loaded.  Two rows are in
 // flight per warp iteration to keep enough loads outstanding; the grid is a multiple of the SM count and
 // warps stride over rows.
+#include <stdlib.h>
+
 #include "ffr_common.cuh"
 
 namespace ffr {
@@ -96,6 +98,64 @@ l2norm_rows_vec_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t di
     }
 }
 
+// Short rows (dim 128 / 256), fp16 output only: a row is owned by L = dim / 16 lanes (4 float4 each), so a warp
+// instruction covers 32 / L rows and the sum of squares needs log2(L) shuffles.  The warp-per-row kernel above spends
+// ~70 instructions per 128-d row (five shuffles, a sqrt and four IEEE divisions per lane for ONE float4) and is issue
+// bound at 3.2 TB/s; here a row costs ~15.  One IEEE reciprocal per row, then multiplies (<= 1.5 ulp from x / |x| before
+// the fp16 rounding -- the same arithmetic as K2's normaliser warps).
+template <int L>
+__global__ void __launch_bounds__(kThreads)
+l2norm_rows_sub_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t dim, __half* __restrict__ y16_a, int32_t ld16,
+                       const L2Second sec) {
+    constexpr int kRowsPerWarp = 32 / L;
+    constexpr int kGroups = 2;                                      // row groups in flight per warp (4 KB)
+    const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
+    const int64_t rows = rows_a + sec.rows;
+    for (int64_t r0 = warp * (kGroups * kRowsPerWarp); r0 < rows; r0 += nwarps * (kGroups * kRowsPerWarp)) {
+        float4 v[kGroups][4];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int64_t r = r0 + g * kRowsPerWarp + rsel;
+            if (r < rows) {
+                const float4* p = reinterpret_cast<const float4*>(r < rows_a ? x_a + r * dim : sec.x + (r - rows_a) * dim);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[g][j] = ldg_stream_f4(p + sub + L * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[g][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int64_t r = r0 + g * kRowsPerWarp + rsel;
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ss = fmaf(v[g][j].x, v[g][j].x, ss); ss = fmaf(v[g][j].y, v[g][j].y, ss);
+                ss = fmaf(v[g][j].z, v[g][j].z, ss); ss = fmaf(v[g][j].w, v[g][j].w, ss);
+            }
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float inv = __fdiv_rn(1.0f, sqrtf(ss));
+            if (r < rows) {
+                __half* y = (r < rows_a) ? y16_a + r * ld16 : sec.y16 + (r - rows_a) * ld16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __half2 h0 = __floats2half2_rn(v[g][j].x * inv, v[g][j].y * inv);
+                    const __half2 h1 = __floats2half2_rn(v[g][j].z * inv, v[g][j].w * inv);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    reinterpret_cast<uint2*>(y)[sub + L * j] = pk;
+                }
+            }
+        }
+    }
+}
+
 // any dim: one warp per row, scalar accesses (row may be unaligned for float4)
 __global__ void __launch_bounds__(kThreads)
 l2norm_rows_generic_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t dim,
@@ -131,7 +191,8 @@ static int launch_l2norm_impl(const float* x, int64_t rows, int32_t dim, __half*
     const int64_t warps_needed = (rows + sec.rows + kRowsPerIter - 1) / kRowsPerIter;
     const int64_t blocks_needed = (warps_needed + (kThreads / 32) - 1) / (kThreads / 32);
     // up to 8 resident CTAs per SM (2048 threads); whole multiples of the SM count when the matrix is big
-    int64_t grid = blocks_needed < static_cast<int64_t>(sms) * 8 ? blocks_needed : static_cast<int64_t>(sms) * 8;
+    static const int k1_bps = getenv("FFR_K1_BLOCKS_PER_SM") ? atoi(getenv("FFR_K1_BLOCKS_PER_SM")) : 8;
+    int64_t grid = blocks_needed < static_cast<int64_t>(sms) * k1_bps ? blocks_needed : static_cast<int64_t>(sms) * k1_bps;
     if (grid < 1) grid = 1;
     const bool vec_ok = (dim % 128 == 0) && (y16 == nullptr || (ld16 % 4 == 0)) &&
                         ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
@@ -140,7 +201,25 @@ static int launch_l2norm_impl(const float* x, int64_t rows, int32_t dim, __half*
                         (sec.rows == 0 || ((reinterpret_cast<uintptr_t>(sec.x) & 15) == 0 &&
                                            (reinterpret_cast<uintptr_t>(sec.y16) & 7) == 0));
     const dim3 g(static_cast<unsigned>(grid)), b(kThreads);
-    if (vec_ok && dim == 128)       l2norm_rows_vec_kernel<1, 8><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    const bool sub_ok = vec_ok && y32 == nullptr && norms == nullptr && y16 != nullptr && ld16 == dim &&
+                        !(getenv("FFR_K1_SUBWARP") && atoi(getenv("FFR_K1_SUBWARP")) == 0);
+    if (sub_ok && (dim == 128 || dim == 256)) {
+        // 8 rows (dim 128) / 4 rows (dim 256) per warp iteration
+        const int64_t rows_per_warp = (dim == 128 ? 4 : 2) * 2;
+        const int64_t w_needed = (rows + sec.rows + rows_per_warp - 1) / rows_per_warp;
+        int64_t gsub = (w_needed + (kThreads / 32) - 1) / (kThreads / 32);
+        if (gsub > static_cast<int64_t>(sms) * 8) gsub = static_cast<int64_t>(sms) * 8;
+        if (gsub < 1) gsub = 1;
+        const dim3 gs(static_cast<unsigned>(gsub));
+        if (dim == 128) l2norm_rows_sub_kernel<8><<<gs, b, 0, s>>>(x, rows, dim, y16, ld16, sec);
+        else            l2norm_rows_sub_kernel<16><<<gs, b, 0, s>>>(x, rows, dim, y16, ld16, sec);
+        FFR_LAUNCH_CHECK("l2norm_rows_sub");
+        return FFR_OK;
+    }
+    static const int k1_rows = getenv("FFR_K1_ROWS") ? atoi(getenv("FFR_K1_ROWS")) : 8;      // experiments: rows in flight at dim 128
+    if (vec_ok && dim == 128 && k1_rows == 2)      l2norm_rows_vec_kernel<1, 2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 128 && k1_rows == 4) l2norm_rows_vec_kernel<1, 4><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
+    else if (vec_ok && dim == 128)  l2norm_rows_vec_kernel<1, 8><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
     else if (vec_ok && dim == 256)  l2norm_rows_vec_kernel<2, 4><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
     else if (vec_ok && dim == 384)  l2norm_rows_vec_kernel<3, 2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
     else if (vec_ok && dim == 512)  l2norm_rows_vec_kernel<4, 2><<<g, b, 0, s>>>(x, rows, dim, y16, ld16, y32, norms, sec);
