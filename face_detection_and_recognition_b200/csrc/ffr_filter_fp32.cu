@@ -15,6 +15,8 @@
 // per lane -- always true for the reference's n_ref = 1 -- else L1/L2-resident global loads), reduces
 // each score with warp shuffles, and keeps a running best with strict comparison in ascending index
 // order, which is np.argmax / np.argmin first-occurrence.
+#include <stdlib.h>
+
 #include "ffr_common.cuh"
 
 namespace ffr {
@@ -148,6 +150,102 @@ filter_fp32_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __
     }
 }
 
+// Short rows (dim 128 / 256) against one or two references -- the reference's literal mode (one mean vector): a candidate
+// row is owned by L = dim / 16 lanes (4 float4 each), so a warp instruction covers 32 / L rows and a score needs log2(L)
+// shuffles instead of five.  The warp-per-row kernel above is issue bound at ~84 % of the HBM copy rate for 128-d rows;
+// here the same bytes cost a third of the instructions.  Same per-pair formulas; the references (and |r|) live in
+// registers.
+template <int L, bool kCosine>
+__global__ void __launch_bounds__(kThreads)
+filter_fp32_sub_kernel(const float* __restrict__ ref, int32_t n_ref, const float* __restrict__ cand, int64_t n_cand,
+                       int32_t dim, float thr, int64_t ref_index_base,
+                       uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx, float* __restrict__ best_val,
+                       BandOut band) {
+    constexpr int kRowsPerWarp = 32 / L;
+    constexpr int kGroups = 2;                                      // row groups in flight per warp (4 KB)
+    const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    float4 rr[2][4];
+    float r_sqrt[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float b = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rr[i][j] = (i < n_ref) ? __ldg(reinterpret_cast<const float4*>(ref + static_cast<int64_t>(i) * dim) + sub + L * j)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            b = fmaf(rr[i][j].x, rr[i][j].x, b); b = fmaf(rr[i][j].y, rr[i][j].y, b);
+            b = fmaf(rr[i][j].z, rr[i][j].z, b); b = fmaf(rr[i][j].w, rr[i][j].w, b);
+        }
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        r_sqrt[i] = __fsqrt_rn(b);
+    }
+    for (int64_t r0 = warp * (kGroups * kRowsPerWarp); r0 < n_cand; r0 += nwarps * (kGroups * kRowsPerWarp)) {
+        float4 c[kGroups][4];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int64_t row = r0 + g * kRowsPerWarp + rsel;
+            const float4* p = reinterpret_cast<const float4*>(cand + (row < n_cand ? row : n_cand - 1) * dim);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[g][j] = ldg_stream_f4(p + sub + L * j);
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int64_t row = r0 + g * kRowsPerWarp + rsel;
+            float cc_sqrt = 0.f;
+            if (kCosine) {
+                float cc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cc = fmaf(c[g][j].x, c[g][j].x, cc); cc = fmaf(c[g][j].y, c[g][j].y, cc);
+                    cc = fmaf(c[g][j].z, c[g][j].z, cc); cc = fmaf(c[g][j].w, c[g][j].w, cc);
+                }
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+                cc_sqrt = __fsqrt_rn(cc);
+            }
+            float best = kCosine ? -INFINITY : INFINITY;
+            int32_t bi = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i < n_ref) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (kCosine) {
+                            a = fmaf(c[g][j].x, rr[i][j].x, a); a = fmaf(c[g][j].y, rr[i][j].y, a);
+                            a = fmaf(c[g][j].z, rr[i][j].z, a); a = fmaf(c[g][j].w, rr[i][j].w, a);
+                        } else {
+                            float d;
+                            d = c[g][j].x - rr[i][j].x; a = fmaf(d, d, a);
+                            d = c[g][j].y - rr[i][j].y; a = fmaf(d, d, a);
+                            d = c[g][j].z - rr[i][j].z; a = fmaf(d, d, a);
+                            d = c[g][j].w - rr[i][j].w; a = fmaf(d, d, a);
+                        }
+                    }
+#pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    const float sc = kCosine ? __fdiv_rn(a, __fmul_rn(r_sqrt[i], cc_sqrt)) : __fsqrt_rn(a);
+                    const bool better = kCosine ? (sc > best) : (sc < best);
+                    if (better || i == 0) { best = sc; bi = i; }
+                }
+            }
+            if (sub == 0 && row < n_cand) {
+                const bool k = kCosine ? (best >= thr) : (best <= thr);
+                keep[row] = k ? 1 : 0;
+                best_idx[row] = static_cast<int32_t>(bi + ref_index_base);
+                if (best_val != nullptr) best_val[row] = best;
+                if (band.count != nullptr && fabsf(best - thr) <= band.tol) {
+                    const int32_t slot = atomicAdd(band.count, 1);
+                    if (band.rows != nullptr && slot < band.cap) band.rows[slot] = row;
+                }
+            }
+        }
+    }
+}
+
 // catch-all: any dim / alignment; one warp per candidate, scalar loads
 template <bool kCosine>
 __global__ void __launch_bounds__(kThreads)
@@ -263,6 +361,23 @@ int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64
         if (cosine) filter_fp32_generic_kernel<true><<<g, kThreads, 0, s>>>(ref, n_ref, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
         else        filter_fp32_generic_kernel<false><<<g, kThreads, 0, s>>>(ref, n_ref, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
         FFR_LAUNCH_CHECK("filter_fp32_generic");
+        return FFR_OK;
+    }
+    if (n_ref <= 2 && (dim == 128 || dim == 256) && !(getenv("FFR_K2S_SUBWARP") && atoi(getenv("FFR_K2S_SUBWARP")) == 0)) {
+        const int64_t rows_per_warp = (dim == 128 ? 4 : 2) * 2;
+        const int64_t w_needed = (n_cand + rows_per_warp - 1) / rows_per_warp;
+        int64_t gsub = (w_needed + (kThreads / 32) - 1) / (kThreads / 32);
+        if (gsub > static_cast<int64_t>(sms) * 8) gsub = static_cast<int64_t>(sms) * 8;
+        const dim3 gs(static_cast<unsigned>(gsub));
+        const int32_t nr = static_cast<int32_t>(n_ref);
+        if (dim == 128) {
+            if (cosine) filter_fp32_sub_kernel<8, true><<<gs, kThreads, 0, s>>>(ref, nr, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
+            else        filter_fp32_sub_kernel<8, false><<<gs, kThreads, 0, s>>>(ref, nr, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
+        } else {
+            if (cosine) filter_fp32_sub_kernel<16, true><<<gs, kThreads, 0, s>>>(ref, nr, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
+            else        filter_fp32_sub_kernel<16, false><<<gs, kThreads, 0, s>>>(ref, nr, cand, n_cand, dim, thr, ref_index_base, keep, idx, val, band);
+        }
+        FFR_LAUNCH_CHECK("filter_fp32_sub");
         return FFR_OK;
     }
     const int nv = (dim + 127) / 128;
