@@ -123,7 +123,9 @@ def test_reference_main_golden(ops, golden_dir, name):
 @pytest.mark.parametrize("n_ref,n_cand,dim,metric", [
     (1, 1000, 128, "euclid"), (1, 777, 512, "euclid"), (1, 50, 100, "euclid"), (3, 500, 128, "euclid"),
     (8, 300, 128, "cosine"), (2, 301, 512, "cosine"), (5, 64, 256, "cosine"), (40, 200, 128, "euclid"),
-    (33, 100, 36, "cosine"), (4, 129, 1024, "euclid"), (6, 10, 2048, "cosine")])
+    (33, 100, 36, "cosine"), (4, 129, 1024, "euclid"), (6, 10, 2048, "cosine"),
+    # dim 128 / 256 with <= 2 references: the sub-warp-per-row kernel (ragged row counts, both metrics)
+    (1, 1001, 256, "euclid"), (2, 515, 128, "cosine"), (2, 77, 256, "cosine"), (1, 3, 128, "cosine"), (2, 4099, 128, "euclid")])
 def test_filter_fp32_small(ops, n_ref, n_cand, dim, metric):
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref + n_cand + dim, unit_norm=(metric == "cosine"))
     from face_detection_and_recognition_b200.ops import FLAG_FORCE_FP32
@@ -186,7 +188,8 @@ def test_mma_raw_scores(ffr_lib, ops, n_ref, n_cand, dim):
 @pytest.mark.parametrize("n_ref,n_cand,dim", [
     (9, 100, 128), (255, 1000, 128), (256, 1000, 128), (257, 1000, 128), (1000, 5000, 128), (300, 129, 512),
     (2000, 3000, 512), (513, 1, 256), (64, 4000, 64), (700, 900, 200), (1111, 2049, 384), (300, 500, 50), (100, 257, 3),
-    (40, 1000, 510)])
+    (40, 1000, 510),
+    (9000, 600, 128)])          # > 8192 references: the sequential update path (update_chunk), not the batched one
 def test_filter_mma_vs_oracle(ops, n_ref, n_cand, dim):
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref * 7 + dim, n_adversarial=min(200, n_cand // 4),
                                       n_dup_refs=min(32, n_ref // 4))
