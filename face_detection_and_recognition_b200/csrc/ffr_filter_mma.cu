@@ -329,6 +329,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint32_t* cons_count = tmem_slot + 3;                            // kNorm: candidate tiles whose A loads have been issued
     float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
 
+    unsigned long long ts_entry = 0;
+    if (p.prof != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_entry));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
@@ -355,6 +357,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     if (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.prof != nullptr && threadIdx.x == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.prof[blockIdx.x * 16 + 12] = ts - ts_entry;                  // ns: entry -> setup done (barriers, TMEM, cluster sync)
+        p.prof[blockIdx.x * 16 + 15] = ts_entry;
+    }
 
     if (warp == 0) {
         // ===================== TMA producer: ONE elected thread runs the whole loop =====================
@@ -771,7 +779,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             p.prof[blockIdx.x * 16 + 10] = static_cast<unsigned long long>(clock64() - t_begin);
             p.prof[blockIdx.x * 16 + 11] = w_tfull;
             p.prof[blockIdx.x * 16 + 3] = c_hot;
-            p.prof[blockIdx.x * 16 + 9] = c_gen;
+            (void)c_gen;
         }
         // balance the last bar.arrive(2) of the lower half so no barrier state is left pending
         if (h != 0 && !first_tile) named_bar_sync(2, kEW * 32);
@@ -783,6 +791,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         tc_fence_after();
         if (kCG == 2) tmem_dealloc_cg2<kTmemCols>(tmem_base);
         else          tmem_dealloc<kTmemCols>(tmem_base);
+    }
+    if (p.prof != nullptr && threadIdx.x == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.prof[blockIdx.x * 16 + 9] = ts;                              // ns: CTA exit
     }
 }
 

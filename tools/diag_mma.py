@@ -97,8 +97,12 @@ def prof(n_ref, n_cand, dim):
           f"t_empty {ml[6] / ml[4]:.1%}, b_full {ml[7] / ml[4]:.1%}")
     print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
           f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
-    if m[3] + m[9] > 0:
-        print(f"      epilogue w4 per ref tile: hot loop {m[3] / tiles:.0f}, general loop {m[9] / tiles:.0f} cyc", flush=True)
+    if m[3] > 0:
+        print(f"      epilogue w4 per ref tile: hot loop {m[3] / tiles:.0f} cyc", flush=True)
+    if m[12] > 0:
+        ent = b[:, 15]
+        print(f"    setup (entry -> barriers/TMEM/cluster sync done): mean {m[12] / 1e3:.2f} us, max {b[:, 12].max().item() / 1e3:.2f} us; "
+              f"CTA entry spread {(ent.max() - ent.min()).item() / 1e3:.2f} us; first entry -> last exit {(b[:, 9].max() - ent.min()).item() / 1e3:.2f} us", flush=True)
     if m[13] > 0:
         print(f"    normaliser 0: total {m[13]:.3e} cyc for {m[14]:.0f} candidate tiles ({m[13] / max(m[14], 1):.0f} per tile); "
               f"TMA thread waited for it {m[12] / m[0]:.1%}", flush=True)
