@@ -227,7 +227,8 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
 
 
 @pytest.mark.parametrize("n_ref,n_cand,dim", [(300, 5000, 128), (1000, 3001, 256), (64, 700, 64), (500, 129, 192),
-                                              (300, 60_000, 128), (700, 45_000, 512), (257, 40_001, 320)])
+                                              (300, 60_000, 128), (700, 45_000, 512), (257, 40_001, 320),
+                                              (90, 38_000 + 100, 260), (33, 19_000 + 129, 64), (64, 512 * 74 + 77, 128)])
 def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
     """K2 with in-kernel normalisation of the candidates (two normaliser warps write the fp16 rows of the CTA's next tile
     into the workspace while the tensor core works; default for large reference sets, forced here with FFR_FUSE_K1=1):
@@ -306,3 +307,12 @@ def test_a_operand_in_tensor_memory_variant(ops, monkeypatch, n_ref, n_cand, dim
     monkeypatch.setenv("FFR_A_TMEM", "1")
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=3 * dim + n_ref, n_adversarial=100, n_dup_refs=8)
     _check_cosine(ops, ref, cand, 0.5)
+
+
+def test_fused_normalisation_is_the_default_for_large_reference_sets(ops):
+    """Above 24 reference tiles and ~76 k candidates ffr_filter drops the K1 pass over the candidates on its own (two
+    launches besides K3: K1 over the references + K2): checked on a ragged shape against the oracle."""
+    n_ref, n_cand, dim = 6500, 75_777 + 300, 128
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=11, n_adversarial=500, n_dup_refs=50, unit_norm=False)
+    res = _check_cosine(ops, ref, cand, 0.5)
+    assert res.stats["launches"] == 3 and res.stats["path"] == "tcgen05"
