@@ -294,7 +294,7 @@ struct KParams {
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
-    unsigned long long* prof;      // optional [gridDim.x][16] stall-cycle counters (diagnostics)
+    unsigned long long* prof;      // optional [gridDim.x][32] stall-cycle counters (diagnostics)
 };
 
 // kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8) = 4 TMEM lane quadrants x kEW/4 column parts.
@@ -360,8 +360,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     if (p.prof != nullptr && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-        p.prof[blockIdx.x * 16 + 12] = ts - ts_entry;                  // ns: entry -> setup done (barriers, TMEM, cluster sync)
-        p.prof[blockIdx.x * 16 + 15] = ts_entry;
+        p.prof[blockIdx.x * 32 + 12] = ts - ts_entry;                  // ns: entry -> setup done (barriers, TMEM, cluster sync)
+        p.prof[blockIdx.x * 32 + 15] = ts_entry;
     }
 
     if (warp == 0) {
@@ -421,9 +421,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
             if (pr) {
-                p.prof[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
-                p.prof[blockIdx.x * 16 + 1] = w_aempty;
-                p.prof[blockIdx.x * 16 + 2] = w_bempty;
+                p.prof[blockIdx.x * 32 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
+                p.prof[blockIdx.x * 32 + 1] = w_aempty;
+                p.prof[blockIdx.x * 32 + 2] = w_bempty;
             }
         }
         __syncwarp();
@@ -496,11 +496,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
             if (pr) {
-                p.prof[blockIdx.x * 16 + 4] = static_cast<unsigned long long>(clock64() - t_begin);
-                p.prof[blockIdx.x * 16 + 5] = w_afull;
-                p.prof[blockIdx.x * 16 + 6] = w_tempty;
-                p.prof[blockIdx.x * 16 + 7] = w_bfull;
-                p.prof[blockIdx.x * 16 + 8] = t_it;
+                p.prof[blockIdx.x * 32 + 4] = static_cast<unsigned long long>(clock64() - t_begin);
+                p.prof[blockIdx.x * 32 + 5] = w_afull;
+                p.prof[blockIdx.x * 32 + 6] = w_tempty;
+                p.prof[blockIdx.x * 32 + 7] = w_bfull;
+                p.prof[blockIdx.x * 32 + 8] = t_it;
             }
         }
         __syncwarp();
@@ -589,8 +589,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             ++n_done;
         }
         if (pr && lane == 0) {
-            p.prof[blockIdx.x * 16 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
-            p.prof[blockIdx.x * 16 + 14] = n_done;
+            p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
+            p.prof[blockIdx.x * 32 + 14] = n_done;
         }
     } else {
         // ===================== epilogue: one thread per (candidate row, column half) =====================
@@ -600,7 +600,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         uint32_t t_it = 0;
         bool first_tile = true;
         const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
-        unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0;
+        unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0, c_bar1 = 0, c_tail = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
         const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
         const bool batch_updates = p.batch_updates != 0;         // short reference sets: see update_part
@@ -694,6 +694,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 ++t_it;
             }
             // ---- hand the upper column parts over, merge, emit (named barriers 1/2 among the epilogue threads)
+            const long long t_tail0 = pr ? clock64() : 0;
             if (h != 0) {
                 float* mg = merge + (h - 1) * 8 * kTileM;
                 if (!first_tile) named_bar_sync(2, kEW * 32);                  // merge buffer free again
@@ -708,7 +709,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 __threadfence_block();
                 named_bar_arrive(1, kEW * 32);
             } else {
+                const long long tm0 = pr ? clock64() : 0;
                 named_bar_sync(1, kEW * 32);
+                if (pr) c_bar1 += static_cast<unsigned long long>(clock64() - tm0);
                 float ob[kParts - 1][4];
                 int32_t oi[kParts - 1][3];
 #pragma unroll
@@ -774,11 +777,14 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
             }
             first_tile = false;
+            if (pr) c_tail += static_cast<unsigned long long>(clock64() - t_tail0);
         }
         if (pr && lane == 0) {
-            p.prof[blockIdx.x * 16 + 10] = static_cast<unsigned long long>(clock64() - t_begin);
-            p.prof[blockIdx.x * 16 + 11] = w_tfull;
-            p.prof[blockIdx.x * 16 + 3] = c_hot;
+            p.prof[blockIdx.x * 32 + 16] = c_bar1;
+            p.prof[blockIdx.x * 32 + 17] = c_tail;
+            p.prof[blockIdx.x * 32 + 10] = static_cast<unsigned long long>(clock64() - t_begin);
+            p.prof[blockIdx.x * 32 + 11] = w_tfull;
+            p.prof[blockIdx.x * 32 + 3] = c_hot;
             (void)c_gen;
         }
         // balance the last bar.arrive(2) of the lower half so no barrier state is left pending
@@ -795,7 +801,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     if (p.prof != nullptr && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-        p.prof[blockIdx.x * 16 + 9] = ts;                              // ns: CTA exit
+        p.prof[blockIdx.x * 32 + 9] = ts;                              // ns: CTA exit
     }
 }
 

@@ -72,19 +72,23 @@ def perf(n_ref, n_cand, dim, flags=0, iters=5, metric="cosine", thr=0.5):
           f"keep={res.keep.float().mean().item():.3f}", flush=True)
 
 
-def prof(n_ref, n_cand, dim):
-    """Where does K2's pipeline wait?  Stall cycles of the TMA thread, the MMA thread and one epilogue warp."""
+def prof(n_ref, n_cand, dim, easy=False):
+    """Where does K2's pipeline wait?  Stall cycles of the TMA thread, the MMA thread and one epilogue warp.
+    easy=True: every candidate is a near copy of reference 0, so the running best is final after the first chunk and the
+    update path never runs again -- the epilogue's floor."""
     lib = _lib.load()
     g = torch.Generator(device="cuda").manual_seed(2)
     ref = torch.nn.functional.normalize(torch.randn(n_ref, dim, device="cuda", generator=g))
     cand = torch.nn.functional.normalize(torch.randn(n_cand, dim, device="cuda", generator=g))
+    if easy:
+        cand = torch.nn.functional.normalize(ref[0][None, :] + 0.05 * cand)
     ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
-    buf = torch.zeros(160 * 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(160 * 32, dtype=torch.int64, device="cuda")
     lib.ffr_debug_set_prof(buf.data_ptr())
     ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
     torch.cuda.synchronize()
     lib.ffr_debug_set_prof(None)
-    b = buf.view(160, 16).double()
+    b = buf.view(160, 32).double()
     b = b[b[:, 0] > 0]
     m = b.mean(0)
     lead = b[b[:, 4] > 0]
@@ -98,7 +102,8 @@ def prof(n_ref, n_cand, dim):
     print(f"    epilogue w4: total {m[10]:.3e} cyc; waiting t_full {m[11] / m[10]:.1%} "
           f"(busy {(m[10] - m[11]) / tiles:.0f} cyc per ref tile)", flush=True)
     if m[3] > 0:
-        print(f"      epilogue w4 per ref tile: hot loop {m[3] / tiles:.0f} cyc", flush=True)
+        print(f"      epilogue w4 per ref tile: hot loop {m[3] / tiles:.0f} cyc; end-of-candidate-tile section {m[17] / tiles:.0f} cyc per ref tile "
+              f"(of which waiting for the upper column part {m[16] / tiles:.0f})", flush=True)
     if m[12] > 0:
         ent = b[:, 15]
         print(f"    setup (entry -> barriers/TMEM/cluster sync done): mean {m[12] / 1e3:.2f} us, max {b[:, 12].max().item() / 1e3:.2f} us; "
@@ -133,6 +138,10 @@ if __name__ == "__main__":
         prof(100_000, 300_000, 128)
         prof(1000, 100_000, 128)
         prof(256, 2_000_000, 128)
+    if "--prof-easy" in sys.argv:
+        prof(100_000, 300_000, 128, easy=True)
+        prof(1000, 100_000, 128, easy=True)
+        prof(10_000, 500_000, 256, easy=True)
     if "--prof128" in sys.argv:
         prof(100_000, 300_000, 128)
         prof(1000, 100_000, 128)
