@@ -161,13 +161,88 @@ __device__ __forceinline__ void update_part(const float (&v)[kC][32], const floa
     gate = t.b1 - delta;
 }
 
-__device__ __forceinline__ float chunk_max(const float (&v)[32]) {
-    float s[4];
+// maxima of the four 8-column groups of a chunk: the first level of the chunk's max tree (0.5 instruction per score)
+__device__ __forceinline__ void group_max8(const float (&v)[32], float (&s)[4]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         s[k] = fmax3(fmax3(v[8 * k + 0], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
                      fmaxf(v[8 * k + 6], v[8 * k + 7]));
+}
+
+__device__ __forceinline__ float chunk_max(const float (&v)[32]) {
+    float s[4];
+    group_max8(v, s);
     return fmax3(s[0], s[1], fmaxf(s[2], s[3]));
+}
+
+// maximum of N registers as a tree of 3-input max
+template <int N>
+struct MaxTree {
+    static __device__ __forceinline__ float run(const float (&a)[N]) {
+        constexpr int M = (N + 2) / 3;
+        float b[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            if (3 * i + 2 < N)      b[i] = fmax3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+            else if (3 * i + 1 < N) b[i] = fmaxf(a[3 * i], a[3 * i + 1]);
+            else                    b[i] = a[3 * i];
+        }
+        return MaxTree<M>::run(b);
+    }
+};
+template <>
+struct MaxTree<1> {
+    static __device__ __forceinline__ float run(const float (&a)[1]) { return a[0]; }
+};
+
+// "Grid" form of the update path: straight-line, ~130 instructions per part whatever the data, instead of ~80 per chunk
+// to build column masks.  The kC*32 columns of the part are seen as a (kC*4) x 8 grid: X group a = columns 8a..8a+7 (their
+// maxima sx are the first level of the max tree the hot loop computes anyway), Y group b = the kC*4 columns with
+// (column mod 8) == b.  A column >= w0 puts its X group AND its Y group at >= w0, and an X and a Y group share exactly one
+// column -- so when exactly one X group and one Y group reach the floor there is exactly ONE column inside the window, it
+// is column 8a + b, and its score is the part maximum m: insert it, done.  Only when two groups of either kind reach the
+// floor (two columns of one part within delta of each other, or exact ties: rare) does the thread fall back to the exact
+// per-column masks of update_part.  Same floor, same insertions: results are identical.
+//
+// The epilogue is bound by the ALU pipe (FMNMX / FSETP / SEL / IADD3 issue every other cycle per scheduler) while the FMA
+// pipe idles, so the group tests run THERE: x = sat((s - w1) * 2^60) is 1.0 for s > w1 and 0.0 otherwise (one FFMA.SAT; w1
+// = just below w0, so "> w1" holds for every s >= w0), and acc = sum x * (1 + g/64) is 0 with no group at the floor, 1 + g/64
+// with exactly group g, and >= 2 with several (one FFMA per group, exact in fp32).  (The floor is at most an ulp-ish lower
+// than w0: the window only gets wider, and the fall-back path uses w0 itself.)
+template <int kC>
+__device__ __forceinline__ void update_grid(const float (&v)[kC][32], const float (&sx)[kC][4], const float (&cm)[kC], float m,
+                                            int32_t base0, float delta, Top3& t, float& gate, float& amb) {
+    constexpr float kBig = 1152921504606846976.0f;     // 2^60
+    const float w0 = fmaxf(t.b1, m) - delta;
+    const float w1 = fmaf(fabsf(w0), -1.1920929e-7f, w0) - 1.0e-30f;
+    const float cb = -w1 * kBig;
+    float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < kC; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = c * 4 + k;
+            ax[g & 1] = fmaf(__saturatef(fmaf(sx[c][k], kBig, cb)), 1.0f + static_cast<float>(g) * 0.015625f, ax[g & 1]);
+        }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        float col[kC * 4];
+#pragma unroll
+        for (int c = 0; c < kC; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) col[c * 4 + k] = v[c][8 * k + b];
+        ay[b & 1] = fmaf(__saturatef(fmaf(MaxTree<kC * 4>::run(col), kBig, cb)), 1.0f + static_cast<float>(b) * 0.015625f, ay[b & 1]);
+    }
+    const float sxa = ax[0] + ax[1], sya = ay[0] + ay[1];
+    if (fmaxf(sxa, sya) >= 2.0f) {                     // several columns of this part inside the window (rare)
+        update_part<kC>(v, cm, m, base0, delta, t, gate, amb);
+    } else {
+        // (sums < 1: the part is below the window, or NaN scores of a zero-norm row -- inserting -inf is a no-op)
+        const float ins = fminf(sxa, sya) >= 1.0f ? m : -INFINITY;
+        const int32_t col = __float2int_rn(fmaf(sxa - 1.0f, 512.0f, (sya - 1.0f) * 64.0f));     // 8 a + b
+        top3_insert(t, ins, base0 + col);
+        gate = t.b1 - delta;
+    }
 }
 
 __device__ __forceinline__ void mask_chunk(float (&v)[32], int valid) {
@@ -287,6 +362,8 @@ struct KParams {
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
     int batch_updates;             // epilogue: batched update path (n_ref <= FFR_BATCH_UPDATE_REFS, default 8192)
+    int grid_updates;              // epilogue: unconditional grid update path (n_ref <= FFR_GRID_UPDATE_REFS, default 8192)
+    int grid_gated;                // epilogue: larger reference sets use the grid update path behind the gate (FFR_GRID_GATED, default 1)
     int norm_diag;                 // kNorm diagnostics (timing only, wrong results): 1 = no loads, 2 = no stores (FFR_NORM_DIAG)
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
@@ -604,6 +681,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         // diagnostics (score dump, epilogue modes) only exist in the general loop
         const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
         const bool batch_updates = p.batch_updates != 0;         // short reference sets: see update_part
+        const bool grid_updates = p.grid_updates != 0;           // ... and update_grid
+        const bool grid_gated = p.grid_gated != 0;               // long reference sets: update_grid behind the gate
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -647,14 +726,23 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         for (int cc = 0; cc < kChunksPerPart; ++cc)
                             if (n_left - cc * 32 < 32) mask_chunk(v[cc], n_left - cc * 32);
                     }
-                    float cm[kChunksPerPart];
+                    float cm[kChunksPerPart], sx[kChunksPerPart][4];
 #pragma unroll
-                    for (int cc = 0; cc < kChunksPerPart; ++cc) cm[cc] = chunk_max(v[cc]);
+                    for (int cc = 0; cc < kChunksPerPart; ++cc) {
+                        group_max8(v[cc], sx[cc]);
+                        cm[cc] = fmax3(sx[cc][0], sx[cc][1], fmaxf(sx[cc][2], sx[cc][3]));
+                    }
                     float m = cm[0];
 #pragma unroll
                     for (int cc = 1; cc < kChunksPerPart; ++cc) m = fmaxf(m, cm[cc]);
-                    if (m >= gate) {
-                        if (batch_updates) {
+                    if (grid_updates) {
+                        // short reference sets: some lane of the warp sets a record on nearly every tile, so the update
+                        // runs unconditionally and branch-free (update_grid)
+                        update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, t, gate, amb);
+                    } else if (m >= gate) {
+                        if (grid_gated) {
+                            update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, t, gate, amb);
+                        } else if (batch_updates) {
                             update_part<kChunksPerPart>(v, cm, m, base0, p.delta, t, gate, amb);
                         } else {
 #pragma unroll
@@ -919,6 +1007,8 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
     p.norm_diag = env_int("FFR_NORM_DIAG", 0);
     p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;
+    p.grid_updates = n_ref <= env_int("FFR_GRID_UPDATE_REFS", 8192) ? 1 : 0;
+    p.grid_gated = env_int("FFR_GRID_GATED", 1);
     p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 
