@@ -211,7 +211,7 @@ struct MaxTree<1> {
 // than w0: the window only gets wider, and the fall-back path uses w0 itself.)
 template <int kC>
 __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const float (&sx)[kC][4], const float (&cm)[kC], float m,
-                                            int32_t base0, float delta, Top3& t, float& gate, float& amb) {
+                                            int32_t base0, float delta, bool exact, Top3& t, float& gate, float& amb) {
     constexpr float kBig = 1152921504606846976.0f;     // 2^60
     const float w0 = fmaxf(t.b1, m) - delta;
     const float w1 = fmaf(fabsf(w0), -1.1920929e-7f, w0) - 1.0e-30f;
@@ -234,15 +234,24 @@ __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const floa
         ay[b & 1] = fmaf(__saturatef(fmaf(MaxTree<kC * 4>::run(col), kBig, cb)), 1.0f + static_cast<float>(b) * 0.015625f, ay[b & 1]);
     }
     const float sxa = ax[0] + ax[1], sya = ay[0] + ay[1];
-    if (fmaxf(sxa, sya) >= 2.0f) {                     // several columns of this part inside the window (rare)
+    const bool multi = fmaxf(sxa, sya) >= 2.0f;        // several columns of this part inside the window (rare per thread)
+    if (exact && multi) {
+        // (a fall-back at 8-column granularity -- one divergent region per X group at the floor -- gave fewer full rescans
+        // but was slower than the per-chunk masks: 16 reconvergence regions in the loop body cost more than they save)
         update_part<kC>(v, cm, m, base0, delta, t, gate, amb);
-    } else {
-        // (sums < 1: the part is below the window, or NaN scores of a zero-norm row -- inserting -inf is a no-op)
-        const float ins = fminf(sxa, sya) >= 1.0f ? m : -INFINITY;
-        const int32_t col = __float2int_rn(fmaf(sxa - 1.0f, 512.0f, (sya - 1.0f) * 64.0f));     // 8 a + b
-        top3_insert(t, ins, base0 + col);
-        gate = t.b1 - delta;
+        return;
     }
+    // !exact: no second path at all.  "Rare per thread" is not rare per accumulator stage -- the MMA waits for the slowest
+    // of the 16 warps of a CTA pair, and with ~0.3 % of (row, part) pairs taking a 400-instruction detour most tiles had one.
+    // Instead the part maximum goes in with a placeholder column and the row remembers it in `amb` (as update_chunk does
+    // for several columns of one chunk): if it is still within delta of the final best the row gets the full fp32 rescan,
+    // which recomputes index, score and keep from every reference; if not, nothing of this part matters any more.
+    // (sums < 1: the part is below the window, or NaN scores of a zero-norm row -- inserting -inf is a no-op)
+    const float ins = fminf(sxa, sya) >= 1.0f ? m : -INFINITY;
+    const int32_t col = multi ? 0 : __float2int_rn(fmaf(sxa - 1.0f, 512.0f, (sya - 1.0f) * 64.0f));     // 8 a + b
+    amb = multi ? fmaxf(amb, m) : amb;
+    top3_insert(t, ins, base0 + col);
+    gate = t.b1 - delta;
 }
 
 __device__ __forceinline__ void mask_chunk(float (&v)[32], int valid) {
@@ -363,6 +372,8 @@ struct KParams {
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
     int batch_updates;             // epilogue: batched update path (n_ref <= FFR_BATCH_UPDATE_REFS, default 8192)
     int grid_updates;              // epilogue: unconditional grid update path (n_ref <= FFR_GRID_UPDATE_REFS, default 8192)
+    int grid_exact;                // update_grid: a part with several in-window columns takes the exact per-column path (1) or only
+                                   // flags the row for the full fp32 rescan (0: branch-free; default for dim <= 256, FFR_GRID_EXACT)
     int grid_gated;                // epilogue: larger reference sets use the grid update path behind the gate (FFR_GRID_GATED, default 1)
     int norm_diag;                 // kNorm diagnostics (timing only, wrong results): 1 = no loads, 2 = no stores (FFR_NORM_DIAG)
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
@@ -674,7 +685,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         const int q = warp & 3;                               // TMEM lane quadrant this warp may access
         const int h = (warp - 2) >> 2;                        // column part of every reference tile this warp scans
         const int r_in_tile = q * 32 + lane;
-        uint32_t t_it = 0;
+        uint32_t t_it = 0, c_it = 0;                          // reference tiles / candidate tiles this CTA has finished
+        constexpr bool kAlt = kParts == 2;                    // the two column parts take turns at the merge + emit tail
         bool first_tile = true;
         const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0, c_bar1 = 0, c_tail = 0;
@@ -683,6 +695,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         const bool batch_updates = p.batch_updates != 0;         // short reference sets: see update_part
         const bool grid_updates = p.grid_updates != 0;           // ... and update_grid
         const bool grid_gated = p.grid_gated != 0;               // long reference sets: update_grid behind the gate
+        const bool grid_exact = p.grid_exact != 0;               // several in-window columns in one part: exact masks, or flag the row
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -738,10 +751,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (grid_updates) {
                         // short reference sets: some lane of the warp sets a record on nearly every tile, so the update
                         // runs unconditionally and branch-free (update_grid)
-                        update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, t, gate, amb);
+                        update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
                     } else if (m >= gate) {
                         if (grid_gated) {
-                            update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, t, gate, amb);
+                            update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
                         } else if (batch_updates) {
                             update_part<kChunksPerPart>(v, cm, m, base0, p.delta, t, gate, amb);
                         } else {
@@ -781,11 +794,18 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
                 ++t_it;
             }
-            // ---- hand the upper column parts over, merge, emit (named barriers 1/2 among the epilogue threads)
+            // ---- hand the other column part(s) over, merge, emit.  The merging thread runs ~300 dependent instructions
+            // alone on its scheduler (its partner is already in the next tile's loads), so with two parts the ROLE alternates
+            // from candidate tile to candidate tile: each warp carries the tail every other tile, and since the reader of
+            // tile n is the writer of tile n + 1 the buffer needs no "free again" barrier.  Named barriers couple only the
+            // warps of ONE lane quadrant (ids 1+q / 5+q, alternating with the tile parity so that an early arrive for tile
+            // n + 2 cannot complete tile n's barrier); with CTA-wide barriers every quadrant waited for the slowest warp.
             const long long t_tail0 = pr ? clock64() : 0;
-            if (h != 0) {
-                float* mg = merge + (h - 1) * 8 * kTileM;
-                if (!first_tile) named_bar_sync(2, kEW * 32);                  // merge buffer free again
+            const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
+            const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
+            if (!merger) {
+                float* mg = merge + (kAlt ? 0 : (h - 1) * 8 * kTileM);
+                if (!kAlt && !first_tile) named_bar_sync(5 + q, kParts * 32);  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
                 mg[2 * kTileM + r_in_tile] = t.b3;
@@ -795,10 +815,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mg[6 * kTileM + r_in_tile] = __int_as_float(t.i3);
                 mg[7 * kTileM + r_in_tile] = amb;
                 __threadfence_block();
-                named_bar_arrive(1, kEW * 32);
+                named_bar_arrive(bar_ready, kParts * 32);
             } else {
                 const long long tm0 = pr ? clock64() : 0;
-                named_bar_sync(1, kEW * 32);
+                named_bar_sync(bar_ready, kParts * 32);
                 if (pr) c_bar1 += static_cast<unsigned long long>(clock64() - tm0);
                 float ob[kParts - 1][4];
                 int32_t oi[kParts - 1][3];
@@ -811,7 +831,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     for (int e = 0; e < 3; ++e) oi[pp][e] = __float_as_int(mg[(4 + e) * kTileM + r_in_tile]);
                     amb = fmaxf(amb, mg[7 * kTileM + r_in_tile]);
                 }
-                named_bar_arrive(2, kEW * 32);
+                if (!kAlt) named_bar_arrive(5 + q, kParts * 32);
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
                     if (ob[pp][0] != -INFINITY) top3_merge_insert(t, ob[pp][0], oi[pp][0]);
@@ -865,6 +885,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
             }
             first_tile = false;
+            ++c_it;
             if (pr) c_tail += static_cast<unsigned long long>(clock64() - t_tail0);
         }
         if (pr && lane == 0) {
@@ -875,8 +896,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             p.prof[blockIdx.x * 32 + 3] = c_hot;
             (void)c_gen;
         }
-        // balance the last bar.arrive(2) of the lower half so no barrier state is left pending
-        if (h != 0 && !first_tile) named_bar_sync(2, kEW * 32);
+        // balance the last bar.arrive(5 + q) of the lower part so no barrier state is left pending
+        if (!kAlt && h != 0 && !first_tile) named_bar_sync(5 + q, kParts * 32);
     }
 
     tc_fence_before();
@@ -1009,6 +1030,10 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;
     p.grid_updates = n_ref <= env_int("FFR_GRID_UPDATE_REFS", 8192) ? 1 : 0;
     p.grid_gated = env_int("FFR_GRID_GATED", 1);
+    // The flag-only form turns every same-part near tie into a full fp32 rescan (~ near-tie fraction / parts of the rows):
+    // measured a win only where the epilogue paces the kernel AND there are hundreds of parts (100 k x 128-d: 6.14 -> 5.81 ms
+    // with K3; 1 k / 4 k / 10 k references: K3 loses more than K2 gains).
+    p.grid_exact = env_int("FFR_GRID_EXACT", (dim_pad <= 128 && n_ref >= 32768) ? 0 : 1);
     p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 

@@ -162,6 +162,14 @@ if __name__ == "__main__":
                 prof(*shape)
                 perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
         os.environ.pop("FFR_GRID_GATED")
+    if "--small" in sys.argv:
+        for ex in ("auto",):
+            print(f" FFR_GRID_EXACT={ex}")
+            for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (4000, 400_000, 128), (100_000, 300_000, 128),
+                          (10_000, 500_000, 256), (10_000, 300_000, 512)]:
+                prof(*shape)
+                perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
+                perf(*shape, iters=3)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
