@@ -45,6 +45,7 @@ constexpr int kTileN = 256;          // references per accumulator stage (TMEM c
 constexpr int kBlockK = 64;          // fp16 per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxAStages = 4;
+constexpr int kMaxASlots = 8;        // A ring slots = stages x K-blocks: full/empty barriers are per K-block (see the MMA issuer)
 constexpr int kMaxBStages = 16;
 constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-block of the A tile
 constexpr uint32_t kTmemCols = 512;
@@ -407,8 +408,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint8_t* smem_b = smem_a + static_cast<size_t>(p.a_stages) * a_stage_bytes;
     uint8_t* extra = smem_b + static_cast<size_t>(p.b_stages) * kBStageBytes;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(extra);
-    uint64_t* a_empty = a_full + kMaxAStages;
-    uint64_t* b_full = a_empty + kMaxAStages;
+    uint64_t* a_empty = a_full + kMaxASlots;
+    uint64_t* b_full = a_empty + kMaxASlots;
     uint64_t* b_empty = b_full + kMaxBStages;
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
@@ -431,7 +432,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         tma_prefetch_desc(&tmap_cand);
         tma_prefetch_desc(&tmap_ref);
-        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kMaxASlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         norm_count[0] = 0; norm_count[1] = 0; *cons_count = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
@@ -468,15 +469,23 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 // The B stream does not depend on the candidate tile: it keeps flowing across tile boundaries, and this
                 // tile's A loads go out the moment their stage is free (and, kNorm, the fp16 rows are written) -- probed
                 // without blocking while the thread waits for B slots.
+                // A moves K-block by K-block, each with its own full/empty barrier: the MMA issuer hands a K-block back as soon
+                // as the LAST reference tile's MMAs on it are done, so the next candidate tile's A streams in behind them
+                // instead of after the whole tile has drained (with one A stage -- dim >= 320 -- that drain + reload was a
+                // ~5 % bubble per candidate tile at dim 512).
                 bool need_a = true;
+                int a_kb = 0;                                 // K-blocks of this tile's A already issued
                 auto try_issue_a = [&]() {
-                    if (kNorm && (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
-                    if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return;
-                    if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
-                    for (int kb = 0; kb < p.kb_count; ++kb) {
-                        uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
-                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
-                        else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                    if (kNorm && a_kb == 0 &&
+                        (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
+                    while (a_kb < p.kb_count) {
+                        const uint32_t slot = as * static_cast<uint32_t>(p.kb_count) + static_cast<uint32_t>(a_kb);
+                        if (!mbar_test_wait(&a_empty[slot], aph ^ 1)) return;
+                        if (leader) mbar_expect_tx(&a_full[slot], kABlockBytes * kCG);   // both CTAs' bytes land on the leader's barrier
+                        uint8_t* dst = smem_a + as * a_stage_bytes + a_kb * kABlockBytes;
+                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[slot], a_kb * kBlockK, row0, kEvictFirst);
+                        else          tma_load_2d(dst, &tmap_cand, &a_full[slot], a_kb * kBlockK, row0, kEvictFirst);
+                        ++a_kb;
                     }
                     if (kNorm) red_release_shared_add(cons_count, 1u);
                     need_a = false;
@@ -530,10 +539,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const uint32_t idesc_full = umma_idesc_f16(kTileM * kCG, kAccN);
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, tph = 0, t_it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-                mbar_wait_timed(&a_full[as], aph, pr, w_afull);
-                tc_fence_after();
+                const uint32_t a_slot0 = as * static_cast<uint32_t>(p.kb_count);
                 const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
                 if constexpr (kTS) {
+                    for (int kb = 0; kb < p.kb_count; ++kb) mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);
+                    tc_fence_after();
                     // staging tile -> tensor memory, one 128 x 32-byte slice per K = 16 step.  tcgen05.cp and tcgen05.mma
                     // execute in issue order, so these copies queue behind the previous tile's MMAs (which still read the
                     // old A columns) and ahead of this tile's; the commit hands the staging tile back to the TMA producer
@@ -544,7 +554,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             tmem_cp_128x256b(tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u,
                                              kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k), kCG == 2);
                     }
-                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + kb]); else umma_commit(&a_empty[a_slot0 + kb]);
+                    }
                 }
                 for (int rt = 0; rt < n_rt; ++rt) {
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
@@ -556,6 +568,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     }
                     const uint32_t d_tmem = tmem_base + acc * kAccN;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
+                        if (!kTS && rt == 0) mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);   // this K-block of A has landed
                         mbar_wait_timed(&b_full[bs], bph, pr, w_bfull);
                         tc_fence_after();
                         const uint32_t b_lo = b_lo_base + bs * (kBStageBytes >> 4);
@@ -572,14 +585,14 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             }
                         }
                         if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
+                        if (!kTS && rt == n_rt - 1) {            // last use of this K-block of A: hand it back to the producer
+                            if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + kb]); else umma_commit(&a_empty[a_slot0 + kb]);
+                        }
                         if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
                     if (kCG == 2) umma_commit_cg2(&t_full[acc]); else umma_commit(&t_full[acc]);       // accumulator ready
                     if (p.acc_stages == 2) { acc ^= 1u; if (acc == 0u) tph ^= 1u; } else { tph ^= 1u; }
                     ++t_it;
-                }
-                if constexpr (!kTS) {
-                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);       // A stage reusable
                 }
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
@@ -994,6 +1007,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     int a_stages = ts ? 1 : env_int("FFR_A_STAGES", a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+    while (a_stages > 1 && a_stages * kb > kMaxASlots) --a_stages;      // one full/empty barrier pair per (stage, K-block)
     // epilogue warps: 8 = 4 TMEM lane quadrants x 2 column parts.  FFR_EPI_WARPS=16 (SS form, cta_group::2 only) splits the
     // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
     const int ew = (cg == 2 && env_int("FFR_EPI_WARPS", 8) == 16 && env_int("FFR_A_TMEM", 0) == 0) ? 16 : 8;

@@ -170,6 +170,14 @@ if __name__ == "__main__":
                 prof(*shape)
                 perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
                 perf(*shape, iters=3)
+    if "--big" in sys.argv:
+        prof(10_000, 1_000_000, 512)
+        prof(10_000, 400_000, 384)
+        perf(10_000, 1_250_000, 512, iters=3)
+        perf(10_000, 1_000_000, 512, flags=ops.FLAG_NO_RECHECK, iters=3)
+        perf(10_000, 400_000, 384, flags=ops.FLAG_NO_RECHECK, iters=3)
+        perf(10_000, 500_000, 256, flags=ops.FLAG_NO_RECHECK, iters=3)
+        perf(100_000, 1_250_000, 128, iters=2)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
