@@ -27,10 +27,11 @@
 //     the fp32 rows of the CTA's next candidate tile into the fp16 workspace (K1 inside K2).
 //   * the accumulator is double buffered in TMEM (2 x 256 of the 512 columns): the MMAs of reference tile
 //     t+1 overlap the epilogue of tile t.
-//   * epilogue per reference tile: four tcgen05.ld in flight -> stage released -> four 3-input-max trees -> one
-//     branch on the tile maximum -> (rarely) update_chunk.  Ascending column order + strict '>' = np.argmax first
-//     occurrence.  The running top-4 (+ the "hidden column" level amb) is what K3 needs to make the index and keep
-//     bit exact in fp32.
+//   * epilogue per reference tile: four tcgen05.ld in flight -> stage released -> four 3-input-max trees -> the update
+//     path update_grid (X/Y group maxima locate the single in-window column; group tests on the FMA pipe), unconditional
+//     for short reference sets, behind one branch on the tile maximum for long ones.  Ascending column order + strict
+//     '>' = np.argmax first occurrence.  The running top-4 (+ the "hidden column" level amb) is what K3 needs to make
+//     the index and keep bit exact in fp32.
 #include <cuda.h>
 #include <stdlib.h>
 

@@ -316,3 +316,73 @@ def test_fused_normalisation_is_the_default_for_large_reference_sets(ops):
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=11, n_adversarial=500, n_dup_refs=50, unit_norm=False)
     res = _check_cosine(ops, ref, cand, 0.5)
     assert res.stats["launches"] == 3 and res.stats["path"] == "tcgen05"
+
+
+# ---------------------------------------------------------------- K2 epilogue variants (round-1d)
+def _near_tie_refs(n_ref, dim, seed, n_pairs):
+    """References with planted near-duplicates (cos gap ~1e-4..1e-3 after fp16 rounding), both inside one 128-column part
+    (offset 3, 9, 40) and across parts / tiles (offset 130, 300): every branch of update_grid sees traffic."""
+    rng = np.random.default_rng(seed)
+    ref = rng.standard_normal((n_ref, dim)).astype(np.float32)
+    for k, off in zip(range(n_pairs), [3, 9, 40, 130, 300] * n_pairs):
+        i = int(rng.integers(0, n_ref - off - 1))
+        ref[i + off] = ref[i] + rng.standard_normal(dim).astype(np.float32) * 0.004
+    return ref
+
+
+@pytest.mark.parametrize("n_ref,n_cand,dim", [(700, 6000, 128), (1500, 3000, 256), (9000, 2500, 128), (300, 40_000, 64)])
+@pytest.mark.parametrize("mode", ["default", "flag_only", "gated", "ungated_r1c"])
+def test_update_grid_variants(ops, monkeypatch, n_ref, n_cand, dim, mode):
+    """update_grid (unconditional / gated), its two fall-backs for several in-window columns in one part (exact per-column
+    masks, or flag-the-row-for-the-full-rescan) and round-1c's per-chunk update paths all meet the same parity bar --
+    on references with planted near-duplicates, so that the fall-backs actually run."""
+    env = {"default": {}, "flag_only": {"FFR_GRID_EXACT": "0"},
+           "gated": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "1"},
+           "ungated_r1c": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_GATED": "0"}}[mode]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ref = _near_tie_refs(n_ref, dim, seed=n_ref + dim, n_pairs=40)
+    rng = np.random.default_rng(n_cand)
+    cand = rng.standard_normal((n_cand, dim)).astype(np.float32)
+    src = rng.integers(0, n_ref, n_cand // 2)
+    cand[::2][: len(src)] = ref[src] + 0.25 * rng.standard_normal((len(src), dim)).astype(np.float32)
+    from face_detection_and_recognition_b200.ops import FLAG_FORCE_MMA
+    res = _check_cosine(ops, ref, cand, 0.5, flags=FLAG_FORCE_MMA)
+    assert res.stats["path"] == "tcgen05"
+    assert res.stats["rechecked"] + res.stats["full_rescans"] > 0
+
+
+def test_update_grid_variants_agree_bitwise(ops, monkeypatch):
+    """Every epilogue variant hands K3 what it needs: after the fp32 re-check the outputs are IDENTICAL, bit for bit."""
+    ref = _near_tie_refs(2000, 128, seed=11, n_pairs=60)
+    rng = np.random.default_rng(12)
+    cand = rng.standard_normal((30_000, 128)).astype(np.float32)
+    cand[::3] = ref[rng.integers(0, 2000, 10_000)] + 0.2 * rng.standard_normal((10_000, 128)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    r_t, c_t = torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev)
+    outs = []
+    for env in ({}, {"FFR_GRID_EXACT": "0"}, {"FFR_GRID_UPDATE_REFS": "0"}, {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_GATED": "0"},
+                {"FFR_CTA_GROUP": "1"}):
+        with monkeypatch.context() as m:
+            for k, v in env.items():
+                m.setenv(k, v)
+            res = ops.face_filter(r_t, c_t, 0.5, want_stats=True)
+            torch.cuda.synchronize()
+            outs.append((res.keep.cpu().numpy().copy(), res.best_idx.cpu().numpy().copy(), res.best_val.cpu().numpy().copy()))
+    gap, _ = _top2_gap64(ref, cand)
+    unamb = gap > TIE_EPS
+    for k, i, v in outs[1:]:
+        assert np.array_equal(k, outs[0][0])
+        assert np.array_equal(i[unamb], outs[0][1][unamb])
+        np.testing.assert_allclose(v, outs[0][2], atol=2e-4)          # un-flagged rows carry the fp16-operand score
+
+
+@pytest.mark.parametrize("tiles_per_cta,dim,n_ref", [(1, 128, 200), (2, 128, 777), (3, 128, 200), (5, 128, 300), (1, 384, 777),
+                                                     (2, 384, 200), (3, 512, 200), (2, 512, 520)])
+def test_candidate_tile_sequences(ops, tiles_per_cta, dim, n_ref):
+    """Odd and even numbers of candidate tiles per CTA (the column halves take turns at the merge + emit tail; the A ring is
+    handed over K-block by K-block, one stage at dim >= 320), with ONE reference tile (first = last) and several."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n_cand = 128 * sms * tiles_per_cta - 37
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + tiles_per_cta + n_ref, n_adversarial=50, n_dup_refs=8)
+    _check_cosine(ops, ref, cand, 0.5)
