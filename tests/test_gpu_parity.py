@@ -324,7 +324,9 @@ def _near_tie_refs(n_ref, dim, seed, n_pairs):
     (offset 3, 9, 40) and across parts / tiles (offset 130, 300): every branch of update_grid sees traffic."""
     rng = np.random.default_rng(seed)
     ref = rng.standard_normal((n_ref, dim)).astype(np.float32)
-    for k, off in zip(range(n_pairs), [3, 9, 40, 130, 300] * n_pairs):
+    offs = [o for o in (3, 9, 40, 130, 300) if o < n_ref - 2]
+    for k in range(n_pairs):
+        off = offs[k % len(offs)]
         i = int(rng.integers(0, n_ref - off - 1))
         ref[i + off] = ref[i] + rng.standard_normal(dim).astype(np.float32) * 0.004
     return ref
