@@ -381,6 +381,7 @@ struct KParams {
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
     int decouple_a;                // producer: A loads issued opportunistically while the B stream runs (FFR_DECOUPLE_A, default on)
+    int a_per_kb;                  // MMA issuer: A K-blocks go back to the producer one by one during the last reference tile (FFR_A_PER_KB, default on)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
@@ -563,9 +564,17 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
                     uint32_t idesc = idesc_full;
-                    if (kCG == 1 && !kTS) {                     // tail reference tile: only as many columns as needed
+                    if (!kTS) {                                 // tail reference tile: only as many columns as needed
                         const int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kAccN;
-                        if (ncols < kAccN) idesc = umma_idesc_f16(kTileM * kCG, static_cast<uint32_t>((ncols + 15) & ~int64_t(15)));
+                        if (ncols < kAccN) {
+                            const uint32_t n16 = static_cast<uint32_t>((ncols + 15) & ~int64_t(15));
+                            // cta_group::2 takes N/2 B rows from EACH CTA (accumulator columns [0, N/2) <- CTA 0's rows,
+                            // [N/2, N) <- CTA 1's): when the live references all sit in CTA 0's half, N = 2 * n16 keeps them
+                            // at their usual columns and the rest (CTA 1's zero-filled rows, stale columns) is masked anyway.
+                            // 10 000 references = 39 tiles + 16: the last tile costs an N = 32 MMA instead of N = 256 (2.2 % of K2).
+                            if (kCG == 1)                 idesc = umma_idesc_f16(kTileM, n16);
+                            else if (2 * n16 < kAccN)     idesc = umma_idesc_f16(kTileM * kCG, 2 * n16);
+                        }
                     }
                     const uint32_t d_tmem = tmem_base + acc * kAccN;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
@@ -586,8 +595,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             }
                         }
                         if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
-                        if (!kTS && rt == n_rt - 1) {            // last use of this K-block of A: hand it back to the producer
-                            if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + kb]); else umma_commit(&a_empty[a_slot0 + kb]);
+                        if (!kTS && rt == n_rt - 1 && (p.a_per_kb || kb == p.kb_count - 1)) {
+                            // last use of this K-block of A: hand it back to the producer (A/B knob: all at the end of the tile)
+                            for (int k2 = p.a_per_kb ? kb : 0; k2 <= kb; ++k2) {
+                                if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + k2]); else umma_commit(&a_empty[a_slot0 + k2]);
+                            }
                         }
                         if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
@@ -1040,6 +1052,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.b_tx_bytes = b_stage / half_b;
     p.discard_a = env_int("FFR_DISCARD_A", 1);
     p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
+    p.a_per_kb = env_int("FFR_A_PER_KB", 1);
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
     p.norm_diag = env_int("FFR_NORM_DIAG", 0);
     p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;

@@ -72,7 +72,7 @@ def perf(n_ref, n_cand, dim, flags=0, iters=5, metric="cosine", thr=0.5):
           f"keep={res.keep.float().mean().item():.3f}", flush=True)
 
 
-def prof(n_ref, n_cand, dim, easy=False):
+def prof(n_ref, n_cand, dim, easy=False, bench_data=False, flags=None):
     """Where does K2's pipeline wait?  Stall cycles of the TMA thread, the MMA thread and one epilogue warp.
     easy=True: every candidate is a near copy of reference 0, so the running best is final after the first chunk and the
     update path never runs again -- the epilogue's floor."""
@@ -82,10 +82,15 @@ def prof(n_ref, n_cand, dim, easy=False):
     cand = torch.nn.functional.normalize(torch.randn(n_cand, dim, device="cuda", generator=g))
     if easy:
         cand = torch.nn.functional.normalize(ref[0][None, :] + 0.05 * cand)
-    ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
+    if bench_data:                       # exactly bench.py's synthetic embeddings (half planted matches)
+        import bench
+        ref = bench.make_refs(n_ref, dim, torch.device("cuda"))
+        cand = bench.make_cands(ref, 0, n_cand, torch.device("cuda"))
+    flags = ops.FLAG_NO_RECHECK if flags is None else flags
+    ops.face_filter(ref, cand, 0.5, flags=flags)
     buf = torch.zeros(160 * 32, dtype=torch.int64, device="cuda")
     lib.ffr_debug_set_prof(buf.data_ptr())
-    ops.face_filter(ref, cand, 0.5, flags=ops.FLAG_NO_RECHECK)
+    ops.face_filter(ref, cand, 0.5, flags=flags)
     torch.cuda.synchronize()
     lib.ffr_debug_set_prof(None)
     b = buf.view(160, 32).double()
@@ -178,6 +183,11 @@ if __name__ == "__main__":
         perf(10_000, 400_000, 384, flags=ops.FLAG_NO_RECHECK, iters=3)
         perf(10_000, 500_000, 256, flags=ops.FLAG_NO_RECHECK, iters=3)
         perf(100_000, 1_250_000, 128, iters=2)
+    if "--benchprof" in sys.argv:
+        # the bench's own cfg3 / cfg4 inputs, re-check on: this round's K2 in cycles
+        prof(10_000, 1_250_000, 512, bench_data=True, flags=0)
+        prof(100_000, 1_250_000, 128, bench_data=True, flags=0)
+        prof(1_000, 100_000, 128, bench_data=True, flags=0)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
