@@ -51,7 +51,10 @@ constexpr int kMaxBStages = 16;
 constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-block of the A tile
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;                       // 227 KiB opt-in maximum
-constexpr uint32_t kBarrierBytes = 512;                       // mbarriers + TMEM slot
+constexpr uint32_t kBarrierBytes = 1024;                      // mbarriers + TMEM slot
+constexpr int kStageRows = 32;                                // stage32: fp32 candidate rows per staging buffer
+constexpr uint32_t kStageBytes = kStageRows * 128 * 4;        // 16 KiB: 32 rows x 128 floats (dim_pad == 128 only)
+constexpr int kMaxSBufs = 6;
 constexpr uint32_t kMergeBytes = kTileM * 8 * 4;              // top-4 + amb hand-over of the upper column half
 // per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
@@ -288,6 +291,16 @@ __device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
         "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)) : "memory");
 }
+// Default semantics (.release at CTA scope) on the leader's barrier: what a producer warp needs after fence.proxy.async when
+// the data it wrote is only ever read through the async proxy (the leader's tcgen05.mma reading THIS CTA's shared memory).
+// The .release.cluster form above costs a MEMBAR.ALL.GPU (~1 us) per arrive.
+__device__ __forceinline__ void mbar_arrive_leader_cta(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1,
                                                 uint64_t cache_hint) {
     asm volatile(
@@ -357,6 +370,19 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
     acc += static_cast<unsigned long long>(clock64() - t0);
 }
 
+// wait with cluster-scope acquire: the arrivals come from the PEER CTA's normaliser warps (stage32), whose generic-proxy
+// shared-memory writes the leader's MMAs are about to read
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (ok == 0);
+}
+
 struct KParams {
     int64_t n_ref, n_cand;
     int32_t kb_count, a_stages, b_stages;
@@ -381,6 +407,9 @@ struct KParams {
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
     int decouple_a;                // producer: A loads issued opportunistically while the B stream runs (FFR_DECOUPLE_A, default on)
+    int stage32;                   // kNorm, dim_pad == 128: fp32 candidate rows are staged through shared memory by TMA and the normaliser
+                                   // warps write the swizzled fp16 A tile directly (no global scratch, no K1 pass at ANY n_ref)
+    int s_bufs;                    // stage32: staging ring depth (buffers of kStageRows rows)
     int a_per_kb;                  // MMA issuer: A K-blocks go back to the producer one by one during the last reference tile (FFR_A_PER_KB, default on)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
@@ -397,7 +426,7 @@ struct KParams {
 template <int kCG, int kEW, bool kNorm, int kAccN>
 __global__ void __launch_bounds__(64 + 32 * kEW + (kNorm ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
-                  const KParams p) {
+                  const __grid_constant__ CUtensorMap tmap_cand32, const KParams p) {
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
     constexpr bool kTS = kAccN != kTileN;                           // A operand in tensor memory (kAccN 192 | 128), else shared memory
     constexpr int kChunksPerPart = (kAccN / 32) / kParts;
@@ -408,14 +437,18 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     const uint32_t a_stage_bytes = static_cast<uint32_t>(p.kb_count) * kABlockBytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + static_cast<size_t>(p.a_stages) * a_stage_bytes;
-    uint8_t* extra = smem_b + static_cast<size_t>(p.b_stages) * kBStageBytes;
+    uint8_t* smem_s = smem_b + static_cast<size_t>(p.b_stages) * kBStageBytes;          // stage32: fp32 staging ring
+    const bool st32 = kNorm && p.stage32 != 0;
+    uint8_t* extra = smem_s + (st32 ? static_cast<size_t>(p.s_bufs) * kStageBytes : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(extra);
     uint64_t* a_empty = a_full + kMaxASlots;
     uint64_t* b_full = a_empty + kMaxASlots;
     uint64_t* b_empty = b_full + kMaxBStages;
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* s_full = t_empty + 2;
+    uint64_t* s_empty = s_full + kMaxSBufs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + kMaxSBufs);
     uint32_t* norm_count = tmem_slot + 1;                            // kNorm: [2] candidate tiles finished by each normaliser warp
     uint32_t* cons_count = tmem_slot + 3;                            // kNorm: candidate tiles whose A loads have been issued
     float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
@@ -434,7 +467,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         tma_prefetch_desc(&tmap_cand);
         tma_prefetch_desc(&tmap_ref);
-        for (int i = 0; i < kMaxASlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        if (st32) tma_prefetch_desc(&tmap_cand32);
+        // stage32: A tiles are completed by the normaliser warps of BOTH CTAs (one arrive per warp) instead of TMA bytes
+        for (int i = 0; i < kMaxASlots; ++i) { mbar_init(&a_full[i], st32 ? 2 * kCG : 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kMaxSBufs; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         norm_count[0] = 0; norm_count[1] = 0; *cons_count = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
@@ -466,18 +502,39 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             unsigned long long w_aempty = 0, w_bempty = 0;
             const long long t_begin = clock64();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, a_it = 0;
+            // stage32: the candidates arrive as fp32 rows in a ring of kStageRows-row staging buffers (four per tile); the
+            // loads run as far ahead as the ring allows, independent of the A stages (the normaliser warps wait for those)
+            const int64_t my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
+            const int64_t s_total = st32 ? my_tiles * (kTileM / kStageRows) : 0;
+            int64_t s_next = 0;
+            uint32_t sb = 0, sph = 0;
+            auto try_issue_s = [&]() {
+                while (s_next < s_total) {
+                    if (!mbar_test_wait(&s_empty[sb], sph ^ 1)) return;
+                    const int64_t t = tile0 + (s_next / (kTileM / kStageRows)) * tile_stride;
+                    const int32_t r0 = static_cast<int32_t>(t * (kTileM * kCG) + cta_rank * kTileM) +
+                                       static_cast<int32_t>(s_next % (kTileM / kStageRows)) * kStageRows;
+                    mbar_expect_tx(&s_full[sb], kStageBytes);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)               // four 32-float (128-byte, swizzled) column groups of the rows
+                        tma_load_2d(smem_s + sb * kStageBytes + g * (kStageBytes / 4), &tmap_cand32, &s_full[sb], g * 32, r0, kEvictFirst);
+                    ++s_next;
+                    if (++sb == static_cast<uint32_t>(p.s_bufs)) { sb = 0; sph ^= 1; }
+                }
+            };
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
                 const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
                 // The B stream does not depend on the candidate tile: it keeps flowing across tile boundaries, and this
-                // tile's A loads go out the moment their stage is free (and, kNorm, the fp16 rows are written) -- probed
-                // without blocking while the thread waits for B slots.
-                // A moves K-block by K-block, each with its own full/empty barrier: the MMA issuer hands a K-block back as soon
-                // as the LAST reference tile's MMAs on it are done, so the next candidate tile's A streams in behind them
-                // instead of after the whole tile has drained (with one A stage -- dim >= 320 -- that drain + reload was a
-                // ~5 % bubble per candidate tile at dim 512).
+                // tile's A loads go out the moment their slots are free (and, kNorm, the fp16 rows are written) -- probed
+                // without blocking while the thread waits for B slots.  A moves K-block by K-block, each with its own
+                // full/empty barrier: the MMA issuer hands a K-block back as soon as the LAST reference tile's MMAs on it are
+                // done, so the next candidate tile's A streams in behind them instead of after the whole tile has drained
+                // (with one A stage -- dim >= 320 -- that drain + reload was a bubble per candidate tile).
                 bool need_a = true;
                 int a_kb = 0;                                 // K-blocks of this tile's A already issued
+                if (st32) need_a = s_next < s_total;
                 auto try_issue_a = [&]() {
+                    if (st32) { try_issue_s(); need_a = s_next < s_total; return; }
                     if (kNorm && a_kb == 0 &&
                         (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
                     while (a_kb < p.kb_count) {
@@ -493,7 +550,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     need_a = false;
                 };
                 try_issue_a();
-                if (!p.decouple_a) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
+                if (!p.decouple_a && !st32) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
                     for (int kb = 0; kb < p.kb_count; ++kb) {
@@ -511,7 +568,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
                 }
-                if (need_a) {                               // fewer B loads than ring slots: nothing made the thread wait
+                if (need_a && !st32) {                      // fewer B loads than ring slots: nothing made the thread wait
                     const long long tw0 = pr ? clock64() : 0;
                     while (need_a) try_issue_a();
                     if (pr) w_aempty += static_cast<unsigned long long>(clock64() - tw0);
@@ -519,6 +576,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 ++a_it;
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
+            while (s_next < s_total) try_issue_s();          // stage32: the last tiles' rows (every B load is out by now)
             if (pr) {
                 p.prof[blockIdx.x * 32 + 0] = static_cast<unsigned long long>(clock64() - t_begin);
                 p.prof[blockIdx.x * 32 + 1] = w_aempty;
@@ -578,7 +636,15 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     }
                     const uint32_t d_tmem = tmem_base + acc * kAccN;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
-                        if (!kTS && rt == 0) mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);   // this K-block of A has landed
+                        if (!kTS && rt == 0) {                                                    // this K-block of A has landed
+                            if (st32) {
+                                const long long tw0 = pr ? clock64() : 0;
+                                mbar_wait_cluster(&a_full[a_slot0 + kb], aph);
+                                if (pr) w_afull += static_cast<unsigned long long>(clock64() - tw0);
+                            } else {
+                                mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);
+                            }
+                        }
                         mbar_wait_timed(&b_full[bs], bph, pr, w_bfull);
                         tc_fence_after();
                         const uint32_t b_lo = b_lo_base + bs * (kBStageBytes >> 4);
@@ -626,6 +692,98 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         // the order the TMA producer will load them; nothing else is waited for (the fp16 rows of different tiles are
         // different memory), so the warps run ahead of the tensor core by as much as their bandwidth allows.
         const int nw = warp - (2 + kEW);
+        if (st32) {
+            // ---- stage32 (dim_pad == 128): rows come out of the TMA-fed fp32 staging ring and go into the A stage as fp16 in the
+            // K-major SWIZZLE_128B layout the MMA descriptors expect (row r of a K-block at r * 128 B, its 16-byte chunk c at
+            // position c ^ (r & 7)) -- exactly what the TMA load of the fp16 workspace would have produced.  HBM sees each
+            // candidate once, as fp32; there is no fp16 scratch and no K1 pass over the candidates whatever n_ref is.
+            // ONE LANE PER ROW: a staging buffer is 32 rows as four 128-byte-wide swizzled column groups, so the eight lanes
+            // of an LDS.128 / STS.128 wavefront hit eight different 16-byte bank groups on the way in and on the way out, and
+            // there is no cross-lane reduction at all (the warp-per-row form spent its time in shuffles and in one
+            // sqrt + division chain per row that the compiler will not interleave: 8-25 k cycles per tile; this is ~1.5 k).
+            // The sum of squares runs in four interleaved chains (not warp_sum's tree): the fp16 rows can differ from the other
+            // forms' by one fp16 ulp in rare elements, like x * (1/|x|) differs from K1's x / |x|.  The two warps take
+            // alternate buffers.
+            const bool pr = p.prof != nullptr && nw == 0;
+            const long long t_nv_begin = clock64();
+            uint32_t as = 0, aph = 0, n_done = 0;
+            unsigned long long w_ae = 0, w_sf = 0;
+            uint32_t g_buf = static_cast<uint32_t>(nw);                                   // staging buffers are numbered in load order
+            const uint32_t sw = (static_cast<uint32_t>(lane) & 7u) << 4;                  // this row's swizzle term
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+                const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
+                for (int kb = 0; kb < p.kb_count; ++kb) mbar_wait_timed(&a_empty[as * p.kb_count + kb], aph ^ 1, pr, w_ae);   // A stage free again
+                for (int part = nw; part < kTileM / kStageRows; part += 2, g_buf += 2) {
+                    const uint32_t sb = g_buf % static_cast<uint32_t>(p.s_bufs);
+                    const uint32_t sph = (g_buf / static_cast<uint32_t>(p.s_bufs)) & 1u;
+                    mbar_wait_timed(&s_full[sb], sph, pr, w_sf);
+                    const uint8_t* src = smem_s + sb * kStageBytes + lane * 128;
+                    // COMPACT loops (eight iterations of four float4 each): fully unrolled, this pass was 10 KB of code that shared
+                    // an instruction cache with the epilogue's hot loop -- both crawled at ~7 cycles per instruction.
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll 1
+                    for (int g = (p.norm_diag & 1) ? 4 : 0; g < 4; ++g) {
+                        const uint8_t* sg = src + g * (kStageBytes / 4);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 x0 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 0) << 4) ^ sw));
+                            const float4 x1 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 1) << 4) ^ sw));
+                            const float4 x2 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 2) << 4) ^ sw));
+                            const float4 x3 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 3) << 4) ^ sw));
+                            q0 = fmaf(x0.x, x0.x, q0); q0 = fmaf(x0.y, x0.y, q0); q0 = fmaf(x0.z, x0.z, q0); q0 = fmaf(x0.w, x0.w, q0);
+                            q1 = fmaf(x1.x, x1.x, q1); q1 = fmaf(x1.y, x1.y, q1); q1 = fmaf(x1.z, x1.z, q1); q1 = fmaf(x1.w, x1.w, q1);
+                            q2 = fmaf(x2.x, x2.x, q2); q2 = fmaf(x2.y, x2.y, q2); q2 = fmaf(x2.z, x2.z, q2); q2 = fmaf(x2.w, x2.w, q2);
+                            q3 = fmaf(x3.x, x3.x, q3); q3 = fmaf(x3.y, x3.y, q3); q3 = fmaf(x3.z, x3.z, q3); q3 = fmaf(x3.w, x3.w, q3);
+                        }
+                    }
+                    const int r = part * kStageRows + lane;                               // row inside the tile
+                    // rows past the end stay zero
+                    const float inv = (row0 + r < p.n_cand) ? __fdiv_rn(1.0f, sqrtf((q0 + q1) + (q2 + q3))) : 0.f;
+                    uint8_t* dst = smem_a + as * a_stage_bytes + r * 128;
+#pragma unroll 1
+                    for (int g = (p.norm_diag & 2) ? 4 : 0; g < 4; ++g) {                 // 32 input floats -> 4 chunks of 8 halves
+                        const uint8_t* sg = src + g * (kStageBytes / 4);
+                        uint8_t* dg = dst + (g >> 1) * kABlockBytes;
+                        // all eight loads first: behind a store to shared memory the compiler will not hoist the next loads
+                        // (same address space), and each pair then waited out its own ~35-cycle latency
+                        float4 x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(c) << 4) ^ sw));
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const __half2 h0 = __floats2half2_rn(x[2 * c].x * inv, x[2 * c].y * inv);
+                            const __half2 h1 = __floats2half2_rn(x[2 * c].z * inv, x[2 * c].w * inv);
+                            const __half2 h2 = __floats2half2_rn(x[2 * c + 1].x * inv, x[2 * c + 1].y * inv);
+                            const __half2 h3 = __floats2half2_rn(x[2 * c + 1].z * inv, x[2 * c + 1].w * inv);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+                            pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(dg + ((static_cast<uint32_t>(4 * (g & 1) + c) << 4) ^ sw)) = pk;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[sb]);                             // the buffer can be refilled
+                }
+                if (!(p.norm_diag & 4)) fence_proxy_async_smem();   // generic-proxy writes of the A tile -> visible to the MMAs (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        if (kCG == 2 && !leader) mbar_arrive_leader_cta(&a_full[as * p.kb_count + kb]);
+                        else                     mbar_arrive(&a_full[as * p.kb_count + kb]);
+                    }
+                }
+                ++n_done;
+                if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
+            }
+            if (pr && lane == 0) {
+                p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
+                p.prof[blockIdx.x * 32 + 14] = n_done;
+                p.prof[blockIdx.x * 32 + 18] = w_ae;
+                p.prof[blockIdx.x * 32 + 19] = w_sf;
+            }
+        } else {
         const int nvec = p.dim >> 2;                                   // float4 per row (dim % 4 == 0 checked on the host)
         const int ld16 = p.kb_count * kBlockK;
         constexpr int kR = 4;                                         // rows in flight per warp
@@ -706,6 +864,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
             p.prof[blockIdx.x * 32 + 14] = n_done;
         }
+        }   // !st32
     } else {
         // ===================== epilogue: one thread per (candidate row, column half) =====================
         const int q = warp & 3;                               // TMEM lane quadrant this warp may access
@@ -974,6 +1133,29 @@ int make_tmap(CUtensorMap* m, const __half* base, int64_t rows, int32_t ld, int3
     return FFR_OK;
 }
 
+// fp32 matrix [rows, dim] row-major (pitch dim * 4 bytes), box = [box_rows, 32 floats = 128 bytes], 128-byte swizzle, zero
+// fill out of bounds (column groups >= dim, rows past the end)
+int make_tmap_f32(CUtensorMap* m, const float* base, int64_t rows, int32_t dim, int32_t box_cols, int32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)"); return FFR_ERR_CUDA; }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 4};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32) failed: CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim); return FFR_ERR_CUDA; }
+    return FFR_OK;
+}
+
+int env_int(const char* name, int dflt);
+
+// stage32 handles rows of 68..128 floats (dim_pad == 128; dim % 4 == 0 is already a condition of fusing)
+bool filter_mma_stage32_ok(int32_t dim, int32_t dim_pad) {
+    return dim_pad == 128 && (dim % 4) == 0 && env_int("FFR_STAGE32", 1) != 0;
+}
+
 unsigned long long* g_prof = nullptr;
 
 int env_int(const char* name, int dflt) {
@@ -1025,14 +1207,22 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
     const int ew = (cg == 2 && env_int("FFR_EPI_WARPS", 8) == 16 && env_int("FFR_A_TMEM", 0) == 0) ? 16 : 8;
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
-    const uint32_t budget = kSmemLimit - extra;
+    // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
+    // MMAs read the other), the B ring gets what is left (>= 2 stages)
+    const bool st32 = fuse && !ts && filter_mma_stage32_ok(dim, dim_pad);
+    int s_bufs = st32 ? kMaxSBufs : 0;
+    if (st32) {
+        a_stages = 2;
+        while (s_bufs > 3 && kSmemLimit - extra - s_bufs * kStageBytes < a_stages * a_stage + 2 * b_stage) --s_bufs;
+    }
+    const uint32_t budget = kSmemLimit - extra - s_bufs * kStageBytes;
     while (a_stages > 1 && a_stages * a_stage + 2 * b_stage > budget) --a_stages;
     if (a_stages * a_stage + 2 * b_stage > budget) { set_error("filter_mma: not enough shared memory for dim %d", dim_pad); return FFR_ERR_UNSUPPORTED; }
     int b_stages = static_cast<int>((budget - a_stages * a_stage) / b_stage);
     if (b_stages > kMaxBStages) b_stages = kMaxBStages;
     const int b_env = env_int("FFR_B_STAGES", 0);
     if (b_env >= 2 && b_env < b_stages) b_stages = b_env;
-    const uint32_t smem = a_stages * a_stage + b_stages * b_stage + extra;
+    const uint32_t smem = a_stages * a_stage + b_stages * b_stage + s_bufs * kStageBytes + extra;
 
     CUtensorMap tm_c, tm_r;
     // FFR_DIAG_HALF_B=1 (timing experiments only, results are wrong): every B load fetches half its rows -- half the L2 -> SM
@@ -1042,6 +1232,11 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (rc != FFR_OK) return rc;
     rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
     if (rc != FFR_OK) return rc;
+    CUtensorMap tm_c32 = tm_c;                                 // (unused placeholder unless stage32)
+    if (st32) {
+        rc = make_tmap_f32(&tm_c32, cand32, n_cand, dim, 32, kStageRows);
+        if (rc != FFR_OK) return rc;
+    }
 
     KParams p;
     p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
@@ -1053,6 +1248,8 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.discard_a = env_int("FFR_DISCARD_A", 1);
     p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
     p.a_per_kb = env_int("FFR_A_PER_KB", 1);
+    p.stage32 = st32 ? 1 : 0;
+    p.s_bufs = s_bufs;
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
     p.norm_diag = env_int("FFR_NORM_DIAG", 0);
     p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;
@@ -1065,7 +1262,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn;
     if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, true, 256> : filter_mma_kernel<2, 16, false, 256>;
     else if (cg == 1)      fn = fuse ? filter_mma_kernel<1, 8, true, 256> : filter_mma_kernel<1, 8, false, 256>;
@@ -1094,7 +1291,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tm_c, tm_r, p));
+    FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tm_c, tm_r, tm_c32, p));
     FFR_LAUNCH_CHECK("filter_mma");
     return FFR_OK;
 }
@@ -1113,7 +1310,10 @@ bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int
     // SM (~7 B/cycle against HBM latency), i.e. ~75 * dim cycles per 128-row tile: hidden with 2x margin from ~20 reference
     // tiles up, whatever the dim.  Few candidate tiles per CTA would expose the first tile's un-hidden pass instead.
     const int64_t n_rt = (n_ref + kTileN - 1) / kTileN;
-    (void)dim_pad;
+    // stage32 (128-d rows): the fp32 rows come through a TMA-fed shared-memory ring, two warps convert a tile in ~4 k cycles
+    // -- hidden behind even ONE reference tile's epilogue -- so the K1 pass over the candidates goes whatever n_ref is
+    if (filter_mma_stage32_ok(dim, dim_pad) && env_int("FFR_CTA_GROUP", 2) == 2)
+        return n_cand >= 4 * static_cast<int64_t>(kTileM) * num_sms();
     return n_rt >= 24 && n_cand >= 4 * static_cast<int64_t>(kTileM) * num_sms();
 }
 

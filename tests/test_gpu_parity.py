@@ -228,11 +228,13 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
 
 @pytest.mark.parametrize("n_ref,n_cand,dim", [(300, 5000, 128), (1000, 3001, 256), (64, 700, 64), (500, 129, 192),
                                               (300, 60_000, 128), (700, 45_000, 512), (257, 40_001, 320),
-                                              (90, 38_000 + 100, 260), (33, 19_000 + 129, 64), (64, 512 * 74 + 77, 128)])
+                                              (90, 38_000 + 100, 260), (33, 19_000 + 129, 64), (64, 512 * 74 + 77, 128),
+                                              (500, 40_000, 100), (1100, 20_001, 72), (260, 57_000, 124)])
 def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
     """K2 with in-kernel normalisation of the candidates (two normaliser warps write the fp16 rows of the CTA's next tile
     into the workspace while the tensor core works; default for large reference sets, forced here with FFR_FUSE_K1=1):
-    same parity bar as K1 + K2, and the same decisions as the K1 + K2 schedule."""
+    same parity bar as K1 + K2, and the same decisions as the K1 + K2 schedule.  Rows of 68..128 floats take the stage32
+    form (fp32 rows staged through shared memory by TMA, fp16 A tile written in place, no global scratch)."""
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + n_ref, n_adversarial=100, n_dup_refs=8, unit_norm=False)
     monkeypatch.setenv("FFR_FUSE_K1", "1")
     res = _check_cosine(ops, ref, cand, 0.5)
@@ -388,3 +390,17 @@ def test_candidate_tile_sequences(ops, tiles_per_cta, dim, n_ref):
     n_cand = 128 * sms * tiles_per_cta - 37
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + tiles_per_cta + n_ref, n_adversarial=50, n_dup_refs=8)
     _check_cosine(ops, ref, cand, 0.5)
+
+
+@pytest.mark.parametrize("stage32", ["1", "0"])
+def test_fused_forms_agree(ops, monkeypatch, stage32):
+    """stage32 and the global-scratch form of the in-kernel normalisation do the same arithmetic per row (one float4 per
+    lane, warp-shuffle sum, one division, multiplies): identical fp16 operands, hence identical outputs as the direct form
+    with FFR_STAGE32=0.  Also covers cta_group::1 (five staging buffers instead of six)."""
+    ref, cand = oracle.make_synthetic(900, 128 * 148 * 2 + 55, 128, seed=3, n_adversarial=200, n_dup_refs=16, unit_norm=False)
+    monkeypatch.setenv("FFR_FUSE_K1", "1")
+    monkeypatch.setenv("FFR_STAGE32", stage32)
+    res = _check_cosine(ops, ref, cand, 0.5)
+    monkeypatch.setenv("FFR_CTA_GROUP", "1")
+    r1 = _check_cosine(ops, ref, cand, 0.5)
+    assert torch.equal(res.keep, r1.keep) and torch.equal(res.best_idx, r1.best_idx)

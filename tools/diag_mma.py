@@ -115,7 +115,7 @@ def prof(n_ref, n_cand, dim, easy=False, bench_data=False, flags=None):
               f"CTA entry spread {(ent.max() - ent.min()).item() / 1e3:.2f} us; first entry -> last exit {(b[:, 9].max() - ent.min()).item() / 1e3:.2f} us", flush=True)
     if m[13] > 0:
         print(f"    normaliser 0: total {m[13]:.3e} cyc for {m[14]:.0f} candidate tiles ({m[13] / max(m[14], 1):.0f} per tile); "
-              f"TMA thread waited for it {m[12] / m[0]:.1%}", flush=True)
+              f"stage32: waiting for the A stage {m[18] / m[13]:.1%}, for staged fp32 rows {m[19] / m[13]:.1%}", flush=True)
 
 
 if __name__ == "__main__":
@@ -188,6 +188,23 @@ if __name__ == "__main__":
         prof(10_000, 1_250_000, 512, bench_data=True, flags=0)
         prof(100_000, 1_250_000, 128, bench_data=True, flags=0)
         prof(1_000, 100_000, 128, bench_data=True, flags=0)
+    if "--stage32" in sys.argv:
+        for st in ("1",):
+            os.environ["FFR_STAGE32"] = st
+            print(f" FFR_STAGE32={st}")
+            for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (64, 4_000_000, 128), (4000, 400_000, 128)]:
+                prof(*shape)
+                perf(*shape, iters=3)
+        os.environ.pop("FFR_STAGE32")
+    if "--st32prof" in sys.argv:
+        for d in ("0", "2"):
+            os.environ["FFR_NORM_DIAG"] = d
+            print(" FFR_NORM_DIAG", d)
+            prof(256, 2_000_000, 128)
+        os.environ.pop("FFR_NORM_DIAG")
+        prof(1000, 100_000, 128)
+        for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (64, 4_000_000, 128), (4000, 400_000, 128)]:
+            perf(*shape, iters=3)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
