@@ -205,7 +205,6 @@ constexpr int kSmallBatch = 8;
 // every flagged row streams the whole reference set once here (no reuse across rows, unlike the tiled walk's 8 rows per
 // reference read): only worth it while that is a few tens of MB of L2 traffic
 constexpr long long kSmallElems = 16000000;
-constexpr int64_t kSmallRefsMax = 256;
 
 __device__ __forceinline__ void
 rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
@@ -296,9 +295,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
     if (count == 0) return;
-    // ... or the reference set is so short that the tiled walk's 1024-reference slices would be mostly padding
-    // (64 references x 4 M candidates: 10.6 k flagged rows took 2.5 ms there)
-    if (static_cast<long long>(count) * n_ref * dim <= kSmallElems || n_ref <= kSmallRefsMax) {
+    if (static_cast<long long>(count) * n_ref * dim <= kSmallElems) {
         rescan_small_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, count, band_tol,
                            band_count, band_rows, band_cap, kVec);
         return;

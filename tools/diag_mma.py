@@ -205,6 +205,9 @@ if __name__ == "__main__":
         prof(1000, 100_000, 128)
         for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (64, 4_000_000, 128), (4000, 400_000, 128)]:
             perf(*shape, iters=3)
+    if "--midn" in sys.argv:
+        for shape in [(64, 4_000_000, 128), (256, 2_000_000, 128), (32, 2_000_000, 128), (500, 1_000_000, 128), (256, 1_000_000, 512)]:
+            perf(*shape, iters=3)
     if "--stream" in sys.argv:
         perf(1, 10_000_000, 128, metric="euclid", thr=1.0)
         perf(1, 4_000_000, 512, metric="euclid", thr=1.0)
