@@ -46,7 +46,6 @@ constexpr int kTileN = 256;          // references per accumulator stage (TMEM c
 constexpr int kBlockK = 64;          // fp16 per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxAStages = 4;
-constexpr int kMaxASlots = 8;        // A ring slots = stages x K-blocks: full/empty barriers are per K-block (see the MMA issuer)
 constexpr int kMaxBStages = 16;
 constexpr uint32_t kABlockBytes = kTileM * kBlockK * 2;      // 16 KiB: one K-block of the A tile
 constexpr uint32_t kTmemCols = 512;
@@ -410,7 +409,6 @@ struct KParams {
     int stage32;                   // kNorm, dim_pad == 128: fp32 candidate rows are staged through shared memory by TMA and the normaliser
                                    // warps write the swizzled fp16 A tile directly (no global scratch, no K1 pass at ANY n_ref)
     int s_bufs;                    // stage32: staging ring depth (buffers of kStageRows rows)
-    int a_per_kb;                  // MMA issuer: A K-blocks go back to the producer one by one during the last reference tile (FFR_A_PER_KB, default on)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
@@ -418,15 +416,19 @@ struct KParams {
 };
 
 // kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8) = 4 TMEM lane quadrants x kEW/4 column parts.
-// kNorm: K1 for the candidates runs INSIDE this kernel.  Two extra "normaliser" warps (the hardware allocates warps in
+// kNormMode != 0 (kNorm): K1 for the candidates runs INSIDE this kernel.  Two extra "normaliser" warps (the hardware allocates warps in
 // fours, so 10 warps cost 12 anyway) read the fp32 rows of the CTA's NEXT candidate tile, L2-normalise them exactly like K1
 // and write the fp16 rows into the workspace, while the tensor core works on the current tile; the TMA producer waits
 // for a per-CTA counter before it loads a tile.  The rows come back through L2, HBM sees the fp32 embeddings once, and
 // the 0.6 ms K1 pass over 1.25 M x 512 disappears behind the MMAs (the kernel needs < 10 % of K1's bandwidth).
-template <int kCG, int kEW, bool kNorm, int kAccN>
-__global__ void __launch_bounds__(64 + 32 * kEW + (kNorm ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
+template <int kCG, int kEW, int kNormMode, int kAccN>
+__global__ void __launch_bounds__(64 + 32 * kEW + (kNormMode ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const __grid_constant__ CUtensorMap tmap_cand32, const KParams p) {
+    // kNormMode: 0 = the candidates' fp16 rows come from K1, 1 = normaliser warps with global loads + fp16 scratch, 2 = stage32.
+    // (Separate instantiations: with stage32 as a run-time branch its mere presence cost the dim-512 kernel 1.5 % of wall clock.)
+    constexpr bool kNorm = kNormMode != 0;
+    constexpr bool st32 = kNormMode == 2;
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
     constexpr bool kTS = kAccN != kTileN;                           // A operand in tensor memory (kAccN 192 | 128), else shared memory
     constexpr int kChunksPerPart = (kAccN / 32) / kParts;
@@ -438,11 +440,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + static_cast<size_t>(p.a_stages) * a_stage_bytes;
     uint8_t* smem_s = smem_b + static_cast<size_t>(p.b_stages) * kBStageBytes;          // stage32: fp32 staging ring
-    const bool st32 = kNorm && p.stage32 != 0;
     uint8_t* extra = smem_s + (st32 ? static_cast<size_t>(p.s_bufs) * kStageBytes : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(extra);
-    uint64_t* a_empty = a_full + kMaxASlots;
-    uint64_t* b_full = a_empty + kMaxASlots;
+    uint64_t* a_empty = a_full + kMaxAStages;
+    uint64_t* b_full = a_empty + kMaxAStages;
     uint64_t* b_empty = b_full + kMaxBStages;
     uint64_t* t_full = b_empty + kMaxBStages;
     uint64_t* t_empty = t_full + 2;
@@ -469,7 +470,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         tma_prefetch_desc(&tmap_ref);
         if (st32) tma_prefetch_desc(&tmap_cand32);
         // stage32: A tiles are completed by the normaliser warps of BOTH CTAs (one arrive per warp) instead of TMA bytes
-        for (int i = 0; i < kMaxASlots; ++i) { mbar_init(&a_full[i], st32 ? 2 * kCG : 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], st32 ? 2 * kCG : 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kMaxSBufs; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         norm_count[0] = 0; norm_count[1] = 0; *cons_count = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -525,26 +526,21 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
                 const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
                 // The B stream does not depend on the candidate tile: it keeps flowing across tile boundaries, and this
-                // tile's A loads go out the moment their slots are free (and, kNorm, the fp16 rows are written) -- probed
-                // without blocking while the thread waits for B slots.  A moves K-block by K-block, each with its own
-                // full/empty barrier: the MMA issuer hands a K-block back as soon as the LAST reference tile's MMAs on it are
-                // done, so the next candidate tile's A streams in behind them instead of after the whole tile has drained
-                // (with one A stage -- dim >= 320 -- that drain + reload was a bubble per candidate tile).
+                // tile's A loads go out the moment their stage is free (and, kNorm, the fp16 rows are written) -- probed
+                // without blocking while the thread waits for B slots.  (Handing A back K-block by K-block during the last
+                // reference tile removed the a_full wait in the in-kernel cycle counts -- 4308 -> 4180 per tile at dim 512 --
+                // but the same-box wall clock of cfg3 got 4 % WORSE, 9.10 -> 9.46 ms: whole stages again.)
                 bool need_a = true;
-                int a_kb = 0;                                 // K-blocks of this tile's A already issued
                 if (st32) need_a = s_next < s_total;
                 auto try_issue_a = [&]() {
                     if (st32) { try_issue_s(); need_a = s_next < s_total; return; }
-                    if (kNorm && a_kb == 0 &&
-                        (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
-                    while (a_kb < p.kb_count) {
-                        const uint32_t slot = as * static_cast<uint32_t>(p.kb_count) + static_cast<uint32_t>(a_kb);
-                        if (!mbar_test_wait(&a_empty[slot], aph ^ 1)) return;
-                        if (leader) mbar_expect_tx(&a_full[slot], kABlockBytes * kCG);   // both CTAs' bytes land on the leader's barrier
-                        uint8_t* dst = smem_a + as * a_stage_bytes + a_kb * kABlockBytes;
-                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[slot], a_kb * kBlockK, row0, kEvictFirst);
-                        else          tma_load_2d(dst, &tmap_cand, &a_full[slot], a_kb * kBlockK, row0, kEvictFirst);
-                        ++a_kb;
+                    if (kNorm && (ld_acquire_shared(&norm_count[0]) <= a_it || ld_acquire_shared(&norm_count[1]) <= a_it)) return;
+                    if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return;
+                    if (leader) mbar_expect_tx(&a_full[as], a_stage_bytes * kCG);    // both CTAs' bytes land on the leader's barrier
+                    for (int kb = 0; kb < p.kb_count; ++kb) {
+                        uint8_t* dst = smem_a + as * a_stage_bytes + kb * kABlockBytes;
+                        if (kCG == 2) tma_load_2d_cg2(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
+                        else          tma_load_2d(dst, &tmap_cand, &a_full[as], kb * kBlockK, row0, kEvictFirst);
                     }
                     if (kNorm) red_release_shared_add(cons_count, 1u);
                     need_a = false;
@@ -599,11 +595,16 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const uint32_t idesc_full = umma_idesc_f16(kTileM * kCG, kAccN);
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, tph = 0, t_it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-                const uint32_t a_slot0 = as * static_cast<uint32_t>(p.kb_count);
+                if (st32) {
+                    const long long tw0 = pr ? clock64() : 0;
+                    mbar_wait_cluster(&a_full[as], aph);
+                    if (pr) w_afull += static_cast<unsigned long long>(clock64() - tw0);
+                } else {
+                    mbar_wait_timed(&a_full[as], aph, pr, w_afull);
+                }
+                tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
                 if constexpr (kTS) {
-                    for (int kb = 0; kb < p.kb_count; ++kb) mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);
-                    tc_fence_after();
                     // staging tile -> tensor memory, one 128 x 32-byte slice per K = 16 step.  tcgen05.cp and tcgen05.mma
                     // execute in issue order, so these copies queue behind the previous tile's MMAs (which still read the
                     // old A columns) and ahead of this tile's; the commit hands the staging tile back to the TMA producer
@@ -614,37 +615,20 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             tmem_cp_128x256b(tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u,
                                              kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k), kCG == 2);
                     }
-                    for (int kb = 0; kb < p.kb_count; ++kb) {
-                        if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + kb]); else umma_commit(&a_empty[a_slot0 + kb]);
-                    }
+                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);
                 }
                 for (int rt = 0; rt < n_rt; ++rt) {
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
                     uint32_t idesc = idesc_full;
-                    if (!kTS) {                                 // tail reference tile: only as many columns as needed
+                    if (kCG == 1 && !kTS) {                     // tail reference tile: only as many columns as needed
+                        // (the cta_group::2 analogue -- N = 2 * ceil16(live) when the live references sit in CTA 0's half --
+                        // is correct but did not pay: an N = 32 MMA costs ~100 cycles, and the same-box wall clock got worse)
                         const int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kAccN;
-                        if (ncols < kAccN) {
-                            const uint32_t n16 = static_cast<uint32_t>((ncols + 15) & ~int64_t(15));
-                            // cta_group::2 takes N/2 B rows from EACH CTA (accumulator columns [0, N/2) <- CTA 0's rows,
-                            // [N/2, N) <- CTA 1's): when the live references all sit in CTA 0's half, N = 2 * n16 keeps them
-                            // at their usual columns and the rest (CTA 1's zero-filled rows, stale columns) is masked anyway.
-                            // 10 000 references = 39 tiles + 16: the last tile costs an N = 32 MMA instead of N = 256 (2.2 % of K2).
-                            if (kCG == 1)                 idesc = umma_idesc_f16(kTileM, n16);
-                            else if (2 * n16 < kAccN)     idesc = umma_idesc_f16(kTileM * kCG, 2 * n16);
-                        }
+                        if (ncols < kAccN) idesc = umma_idesc_f16(kTileM * kCG, static_cast<uint32_t>((ncols + 15) & ~int64_t(15)));
                     }
                     const uint32_t d_tmem = tmem_base + acc * kAccN;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
-                        if (!kTS && rt == 0) {                                                    // this K-block of A has landed
-                            if (st32) {
-                                const long long tw0 = pr ? clock64() : 0;
-                                mbar_wait_cluster(&a_full[a_slot0 + kb], aph);
-                                if (pr) w_afull += static_cast<unsigned long long>(clock64() - tw0);
-                            } else {
-                                mbar_wait_timed(&a_full[a_slot0 + kb], aph, pr, w_afull);
-                            }
-                        }
                         mbar_wait_timed(&b_full[bs], bph, pr, w_bfull);
                         tc_fence_after();
                         const uint32_t b_lo = b_lo_base + bs * (kBStageBytes >> 4);
@@ -661,17 +645,14 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                             }
                         }
                         if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
-                        if (!kTS && rt == n_rt - 1 && (p.a_per_kb || kb == p.kb_count - 1)) {
-                            // last use of this K-block of A: hand it back to the producer (A/B knob: all at the end of the tile)
-                            for (int k2 = p.a_per_kb ? kb : 0; k2 <= kb; ++k2) {
-                                if (kCG == 2) umma_commit_cg2(&a_empty[a_slot0 + k2]); else umma_commit(&a_empty[a_slot0 + k2]);
-                            }
-                        }
                         if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
                     }
                     if (kCG == 2) umma_commit_cg2(&t_full[acc]); else umma_commit(&t_full[acc]);       // accumulator ready
                     if (p.acc_stages == 2) { acc ^= 1u; if (acc == 0u) tph ^= 1u; } else { tph ^= 1u; }
                     ++t_it;
+                }
+                if constexpr (!kTS) {
+                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);       // A stage reusable
                 }
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
@@ -712,7 +693,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const uint32_t sw = (static_cast<uint32_t>(lane) & 7u) << 4;                  // this row's swizzle term
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
                 const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
-                for (int kb = 0; kb < p.kb_count; ++kb) mbar_wait_timed(&a_empty[as * p.kb_count + kb], aph ^ 1, pr, w_ae);   // A stage free again
+                mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_ae);                          // A stage free again
                 for (int part = nw; part < kTileM / kStageRows; part += 2, g_buf += 2) {
                     const uint32_t sb = g_buf % static_cast<uint32_t>(p.s_bufs);
                     const uint32_t sph = (g_buf / static_cast<uint32_t>(p.s_bufs)) & 1u;
@@ -769,10 +750,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (!(p.norm_diag & 4)) fence_proxy_async_smem();   // generic-proxy writes of the A tile -> visible to the MMAs (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    for (int kb = 0; kb < p.kb_count; ++kb) {
-                        if (kCG == 2 && !leader) mbar_arrive_leader_cta(&a_full[as * p.kb_count + kb]);
-                        else                     mbar_arrive(&a_full[as * p.kb_count + kb]);
-                    }
+                    if (kCG == 2 && !leader) mbar_arrive_leader_cta(&a_full[as]);
+                    else                     mbar_arrive(&a_full[as]);
                 }
                 ++n_done;
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
@@ -1202,14 +1181,13 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     int a_stages = ts ? 1 : env_int("FFR_A_STAGES", a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
-    while (a_stages > 1 && a_stages * kb > kMaxASlots) --a_stages;      // one full/empty barrier pair per (stage, K-block)
     // epilogue warps: 8 = 4 TMEM lane quadrants x 2 column parts.  FFR_EPI_WARPS=16 (SS form, cta_group::2 only) splits the
     // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
     const int ew = (cg == 2 && env_int("FFR_EPI_WARPS", 8) == 16 && env_int("FFR_A_TMEM", 0) == 0) ? 16 : 8;
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
     // MMAs read the other), the B ring gets what is left (>= 2 stages)
-    const bool st32 = fuse && !ts && filter_mma_stage32_ok(dim, dim_pad);
+    const bool st32 = fuse && !ts && ew == 8 && filter_mma_stage32_ok(dim, dim_pad);
     int s_bufs = st32 ? kMaxSBufs : 0;
     if (st32) {
         a_stages = 2;
@@ -1247,7 +1225,6 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.b_tx_bytes = b_stage / half_b;
     p.discard_a = env_int("FFR_DISCARD_A", 1);
     p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
-    p.a_per_kb = env_int("FFR_A_PER_KB", 1);
     p.stage32 = st32 ? 1 : 0;
     p.s_bufs = s_bufs;
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
@@ -1264,17 +1241,18 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn;
-    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, true, 256> : filter_mma_kernel<2, 16, false, 256>;
-    else if (cg == 1)      fn = fuse ? filter_mma_kernel<1, 8, true, 256> : filter_mma_kernel<1, 8, false, 256>;
-    else if (acc_n == 256) fn = fuse ? filter_mma_kernel<2, 8, true, 256> : filter_mma_kernel<2, 8, false, 256>;
-    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, true, 192> : filter_mma_kernel<2, 8, false, 192>;
-    else                   fn = fuse ? filter_mma_kernel<2, 8, true, 128> : filter_mma_kernel<2, 8, false, 128>;
+    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, 1, 256> : filter_mma_kernel<2, 16, 0, 256>;
+    else if (cg == 1)      fn = st32 ? filter_mma_kernel<1, 8, 2, 256> : fuse ? filter_mma_kernel<1, 8, 1, 256> : filter_mma_kernel<1, 8, 0, 256>;
+    else if (acc_n == 256) fn = st32 ? filter_mma_kernel<2, 8, 2, 256> : fuse ? filter_mma_kernel<2, 8, 1, 256> : filter_mma_kernel<2, 8, 0, 256>;
+    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, 1, 192> : filter_mma_kernel<2, 8, 0, 192>;
+    else                   fn = fuse ? filter_mma_kernel<2, 8, 1, 128> : filter_mma_kernel<2, 8, 0, 128>;
     static bool attr_set = false;
     if (!attr_set) {
-        KernelFn all[] = {filter_mma_kernel<1, 8, true, 256>, filter_mma_kernel<1, 8, false, 256>, filter_mma_kernel<2, 8, true, 256>,
-                          filter_mma_kernel<2, 8, false, 256>, filter_mma_kernel<2, 8, true, 192>, filter_mma_kernel<2, 8, false, 192>,
-                          filter_mma_kernel<2, 8, true, 128>, filter_mma_kernel<2, 8, false, 128>,
-                          filter_mma_kernel<2, 16, true, 256>, filter_mma_kernel<2, 16, false, 256>};
+        KernelFn all[] = {filter_mma_kernel<1, 8, 1, 256>, filter_mma_kernel<1, 8, 0, 256>, filter_mma_kernel<2, 8, 1, 256>,
+                          filter_mma_kernel<2, 8, 0, 256>, filter_mma_kernel<2, 8, 1, 192>, filter_mma_kernel<2, 8, 0, 192>,
+                          filter_mma_kernel<2, 8, 1, 128>, filter_mma_kernel<2, 8, 0, 128>,
+                          filter_mma_kernel<2, 16, 1, 256>, filter_mma_kernel<2, 16, 0, 256>,
+                          filter_mma_kernel<1, 8, 2, 256>, filter_mma_kernel<2, 8, 2, 256>};
         for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
