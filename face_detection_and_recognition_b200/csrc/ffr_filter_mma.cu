@@ -397,11 +397,9 @@ struct KParams {
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
     int32_t dim;                   // kNorm: true embedding size (row pitch of cand32)
     int acc_stages;                // TMEM accumulator stages in use (2 = MMA of tile t+1 overlaps the epilogue of t)
-    int batch_updates;             // epilogue: batched update path (n_ref <= FFR_BATCH_UPDATE_REFS, default 8192)
     int grid_updates;              // epilogue: unconditional grid update path (n_ref <= FFR_GRID_UPDATE_REFS, default 8192)
     int grid_exact;                // update_grid: a part with several in-window columns takes the exact per-column path (1) or only
                                    // flags the row for the full fp32 rescan (0: branch-free; default for dim <= 256, FFR_GRID_EXACT)
-    int grid_gated;                // epilogue: larger reference sets use the grid update path behind the gate (FFR_GRID_GATED, default 1)
     int norm_diag;                 // kNorm diagnostics (timing only, wrong results): 1 = no loads, 2 = no stores (FFR_NORM_DIAG)
     int norm_evict_first;          // kNorm: fp32 loads carry the L2 evict-first policy (FFR_NORM_EVICT_FIRST)
     int norm_ahead;                // kNorm: tiles the normaliser warps may run ahead of the A loads (FFR_NORM_AHEAD, default 2)
@@ -856,9 +854,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0, c_bar1 = 0, c_tail = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
         const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
-        const bool batch_updates = p.batch_updates != 0;         // short reference sets: see update_part
         const bool grid_updates = p.grid_updates != 0;           // ... and update_grid
-        const bool grid_gated = p.grid_gated != 0;               // long reference sets: update_grid behind the gate
         const bool grid_exact = p.grid_exact != 0;               // several in-window columns in one part: exact masks, or flag the row
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -912,21 +908,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     float m = cm[0];
 #pragma unroll
                     for (int cc = 1; cc < kChunksPerPart; ++cc) m = fmaxf(m, cm[cc]);
-                    if (grid_updates) {
-                        // short reference sets: some lane of the warp sets a record on nearly every tile, so the update
-                        // runs unconditionally and branch-free (update_grid)
-                        update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
-                    } else if (m >= gate) {
-                        if (grid_gated) {
-                            update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
-                        } else if (batch_updates) {
-                            update_part<kChunksPerPart>(v, cm, m, base0, p.delta, t, gate, amb);
-                        } else {
-#pragma unroll
-                            for (int cc = 0; cc < kChunksPerPart; ++cc)
-                                if (cm[cc] >= gate) update_chunk(v[cc], cm[cc], base0 + cc * 32, p.delta, t, gate, amb);
-                        }
-                    }
+                    // short reference sets: some lane of the warp sets a record on nearly every tile, so the update runs
+                    // unconditionally and branch-free; long ones: behind one branch on the part maximum.  (Round-1c's
+                    // per-chunk update paths are gone from this loop: dead code in it costs wall clock.)
+                    if (grid_updates || m >= gate) update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
                     if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
                     // ---- general loop, one chunk at a time: diagnostics only (score dump, epilogue modes)
@@ -1229,9 +1214,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.s_bufs = s_bufs;
     p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
     p.norm_diag = env_int("FFR_NORM_DIAG", 0);
-    p.batch_updates = n_ref <= env_int("FFR_BATCH_UPDATE_REFS", 8192) ? 1 : 0;
     p.grid_updates = n_ref <= env_int("FFR_GRID_UPDATE_REFS", 8192) ? 1 : 0;
-    p.grid_gated = env_int("FFR_GRID_GATED", 1);
     // The flag-only form turns every same-part near tie into a full fp32 rescan (~ near-tie fraction / parts of the rows):
     // measured a win only where the epilogue paces the kernel AND there are hundreds of parts (100 k x 128-d: 6.14 -> 5.81 ms
     // with K3; 1 k / 4 k / 10 k references: K3 loses more than K2 gains).

@@ -335,14 +335,13 @@ def _near_tie_refs(n_ref, dim, seed, n_pairs):
 
 
 @pytest.mark.parametrize("n_ref,n_cand,dim", [(700, 6000, 128), (1500, 3000, 256), (9000, 2500, 128), (300, 40_000, 64)])
-@pytest.mark.parametrize("mode", ["default", "flag_only", "gated", "ungated_r1c"])
+@pytest.mark.parametrize("mode", ["default", "flag_only", "gated"])
 def test_update_grid_variants(ops, monkeypatch, n_ref, n_cand, dim, mode):
     """update_grid (unconditional / gated), its two fall-backs for several in-window columns in one part (exact per-column
-    masks, or flag-the-row-for-the-full-rescan) and round-1c's per-chunk update paths all meet the same parity bar --
-    on references with planted near-duplicates, so that the fall-backs actually run."""
+    masks, or flag-the-row-for-the-full-rescan) all meet the same parity bar -- on references with planted near-duplicates,
+    so that the fall-backs actually run."""
     env = {"default": {}, "flag_only": {"FFR_GRID_EXACT": "0"},
-           "gated": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "1"},
-           "ungated_r1c": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_GATED": "0"}}[mode]
+           "gated": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "1"}}[mode]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     ref = _near_tie_refs(n_ref, dim, seed=n_ref + dim, n_pairs=40)
@@ -365,7 +364,7 @@ def test_update_grid_variants_agree_bitwise(ops, monkeypatch):
     dev = torch.device("cuda:0")
     r_t, c_t = torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev)
     outs = []
-    for env in ({}, {"FFR_GRID_EXACT": "0"}, {"FFR_GRID_UPDATE_REFS": "0"}, {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_GATED": "0"},
+    for env in ({}, {"FFR_GRID_EXACT": "0"}, {"FFR_GRID_UPDATE_REFS": "0"}, {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "0"},
                 {"FFR_CTA_GROUP": "1"}):
         with monkeypatch.context() as m:
             for k, v in env.items():

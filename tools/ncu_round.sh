@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r01b}
 K='regex:l2norm|filter_mma|recheck|filter_fp32|pack_results'
-for w in cfg3 cfg4 cfg1; do
+for w in ${WORKLOADS:-cfg3 cfg4 cfg1}; do
   CMD="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
   $CMD > gpurun_out/plain_$w.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 9 -c 12 --csv \
