@@ -151,22 +151,15 @@ if __name__ == "__main__":
         prof(100_000, 300_000, 128)
         prof(1000, 100_000, 128)
     if "--grid" in sys.argv:
-        # grid update path (update_grid) against the gated update path, per shape
-        for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (4000, 400_000, 128), (10_000, 500_000, 256)]:
+        # grid update path unconditional (every part) against gated (behind one branch on the part maximum), per shape
+        for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (4000, 400_000, 128), (10_000, 500_000, 256),
+                      (100_000, 300_000, 128)]:
             for g in ("0", "1000000"):
                 os.environ["FFR_GRID_UPDATE_REFS"] = g
-                os.environ["FFR_GRID_GATED"] = "0"
                 print(f" FFR_GRID_UPDATE_REFS={g}")
                 prof(*shape)
                 perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
         os.environ.pop("FFR_GRID_UPDATE_REFS")
-        for shape in [(10_000, 500_000, 256), (100_000, 300_000, 128), (10_000, 300_000, 512), (30_000, 300_000, 128)]:
-            for g in ("0", "1"):
-                os.environ["FFR_GRID_GATED"] = g
-                print(f" FFR_GRID_GATED={g}")
-                prof(*shape)
-                perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
-        os.environ.pop("FFR_GRID_GATED")
     if "--small" in sys.argv:
         for ex in ("auto",):
             print(f" FFR_GRID_EXACT={ex}")
