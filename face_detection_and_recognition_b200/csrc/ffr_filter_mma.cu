@@ -419,14 +419,17 @@ struct KParams {
 // and write the fp16 rows into the workspace, while the tensor core works on the current tile; the TMA producer waits
 // for a per-CTA counter before it loads a tile.  The rows come back through L2, HBM sees the fp32 embeddings once, and
 // the 0.6 ms K1 pass over 1.25 M x 512 disappears behind the MMAs (the kernel needs < 10 % of K1's bandwidth).
-template <int kCG, int kEW, int kNormMode, int kAccN>
+template <int kCG, int kEW, int kNormMode, int kAccN, bool kInstr>
 __global__ void __launch_bounds__(64 + 32 * kEW + (kNormMode ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const __grid_constant__ CUtensorMap tmap_cand32, const KParams p) {
     // kNormMode: 0 = the candidates' fp16 rows come from K1, 1 = normaliser warps with global loads + fp16 scratch, 2 = stage32.
     // (Separate instantiations: with stage32 as a run-time branch its mere presence cost the dim-512 kernel 1.5 % of wall clock.)
+    // kInstr: the instrumented build (in-kernel cycle counters, score dump, epilogue diagnostics).  The production
+    // instantiation contains none of it: the counters alone were half a dozen spilled 64-bit values per role.
     constexpr bool kNorm = kNormMode != 0;
     constexpr bool st32 = kNormMode == 2;
+    const unsigned long long* const prof_on = kInstr ? p.prof : nullptr;
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
     constexpr bool kTS = kAccN != kTileN;                           // A operand in tensor memory (kAccN 192 | 128), else shared memory
     constexpr int kChunksPerPart = (kAccN / 32) / kParts;
@@ -453,7 +456,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
 
     unsigned long long ts_entry = 0;
-    if (p.prof != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_entry));
+    if (prof_on != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_entry));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
@@ -483,7 +486,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     if (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (p.prof != nullptr && threadIdx.x == 0) {
+    if (prof_on != nullptr && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
         p.prof[blockIdx.x * 32 + 12] = ts - ts_entry;                  // ns: entry -> setup done (barriers, TMEM, cluster sync)
@@ -497,7 +500,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         // positions and phases are carried incrementally: a runtime `% stages` per K-block is a 25-instruction
         // division with MUFU latency on the critical path of every stage.
         if (elect_one()) {
-            const bool pr = p.prof != nullptr;
+            const bool pr = prof_on != nullptr;
             unsigned long long w_aempty = 0, w_bempty = 0;
             const long long t_begin = clock64();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, a_it = 0;
@@ -581,7 +584,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer: one elected thread of the leader CTA =====================
         if (leader && elect_one()) {
-            const bool pr = p.prof != nullptr;
+            const bool pr = prof_on != nullptr;
             unsigned long long w_afull = 0, w_tempty = 0, w_bfull = 0;
             const long long t_begin = clock64();
             // UMMA smem descriptor, K-major SWIZZLE_128B: hi word is constant (SBO 1024 B, version 1, layout 2);
@@ -683,7 +686,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // The sum of squares runs in four interleaved chains (not warp_sum's tree): the fp16 rows can differ from the other
             // forms' by one fp16 ulp in rare elements, like x * (1/|x|) differs from K1's x / |x|.  The two warps take
             // alternate buffers.
-            const bool pr = p.prof != nullptr && nw == 0;
+            const bool pr = prof_on != nullptr && nw == 0;
             const long long t_nv_begin = clock64();
             uint32_t as = 0, aph = 0, n_done = 0;
             unsigned long long w_ae = 0, w_sf = 0;
@@ -764,7 +767,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         const int nvec = p.dim >> 2;                                   // float4 per row (dim % 4 == 0 checked on the host)
         const int ld16 = p.kb_count * kBlockK;
         constexpr int kR = 4;                                         // rows in flight per warp
-        const bool pr = p.prof != nullptr && nw == 0;
+        const bool pr = prof_on != nullptr && nw == 0;
         const long long t_nv_begin = clock64();
         uint32_t n_done = 0;
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -850,10 +853,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         uint32_t t_it = 0, c_it = 0;                          // reference tiles / candidate tiles this CTA has finished
         constexpr bool kAlt = kParts == 2;                    // the two column parts take turns at the merge + emit tail
         bool first_tile = true;
-        const bool pr = p.prof != nullptr && warp == 4;                 // one part-0 warp reports
+        const bool pr = prof_on != nullptr && warp == 4;                 // one part-0 warp reports
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0, c_bar1 = 0, c_tail = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
-        const bool hot_ok = p.dbg_scores == nullptr && p.epi_mode == 0;
+        const bool hot_ok = !kInstr || (p.dbg_scores == nullptr && p.epi_mode == 0);
         const bool grid_updates = p.grid_updates != 0;           // ... and update_grid
         const bool grid_exact = p.grid_exact != 0;               // several in-window columns in one part: exact masks, or flag the row
         const long long t_begin = clock64();
@@ -1056,7 +1059,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         if (kCG == 2) tmem_dealloc_cg2<kTmemCols>(tmem_base);
         else          tmem_dealloc<kTmemCols>(tmem_base);
     }
-    if (p.prof != nullptr && threadIdx.x == 0) {
+    if (prof_on != nullptr && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
         p.prof[blockIdx.x * 32 + 9] = ts;                              // ns: CTA exit
@@ -1223,19 +1226,32 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (p.norm_ahead < 1) p.norm_ahead = 1;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+    // the instrumented instantiations exist for the default tile shape only (what tools/diag_mma.py and the tests' score dump use)
+    const bool instr = (g_prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0) && ew == 8 && acc_n == 256;
     KernelFn fn;
-    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, 1, 256> : filter_mma_kernel<2, 16, 0, 256>;
-    else if (cg == 1)      fn = st32 ? filter_mma_kernel<1, 8, 2, 256> : fuse ? filter_mma_kernel<1, 8, 1, 256> : filter_mma_kernel<1, 8, 0, 256>;
-    else if (acc_n == 256) fn = st32 ? filter_mma_kernel<2, 8, 2, 256> : fuse ? filter_mma_kernel<2, 8, 1, 256> : filter_mma_kernel<2, 8, 0, 256>;
-    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, 1, 192> : filter_mma_kernel<2, 8, 0, 192>;
-    else                   fn = fuse ? filter_mma_kernel<2, 8, 1, 128> : filter_mma_kernel<2, 8, 0, 128>;
+    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, 1, 256, false> : filter_mma_kernel<2, 16, 0, 256, false>;
+    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, 1, 192, false> : filter_mma_kernel<2, 8, 0, 192, false>;
+    else if (acc_n == 128) fn = fuse ? filter_mma_kernel<2, 8, 1, 128, false> : filter_mma_kernel<2, 8, 0, 128, false>;
+    else if (cg == 1) {
+        if (instr) fn = st32 ? filter_mma_kernel<1, 8, 2, 256, true> : fuse ? filter_mma_kernel<1, 8, 1, 256, true> : filter_mma_kernel<1, 8, 0, 256, true>;
+        else       fn = st32 ? filter_mma_kernel<1, 8, 2, 256, false> : fuse ? filter_mma_kernel<1, 8, 1, 256, false> : filter_mma_kernel<1, 8, 0, 256, false>;
+    } else {
+        if (instr) fn = st32 ? filter_mma_kernel<2, 8, 2, 256, true> : fuse ? filter_mma_kernel<2, 8, 1, 256, true> : filter_mma_kernel<2, 8, 0, 256, true>;
+        else       fn = st32 ? filter_mma_kernel<2, 8, 2, 256, false> : fuse ? filter_mma_kernel<2, 8, 1, 256, false> : filter_mma_kernel<2, 8, 0, 256, false>;
+    }
+    if ((dbg_scores != nullptr || p.epi_mode != 0) && !instr) {
+        set_error("filter_mma: score dump / epilogue diagnostics need the default tile shape (FFR_EPI_WARPS=8, FFR_A_TMEM=0)");
+        return FFR_ERR_UNSUPPORTED;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        KernelFn all[] = {filter_mma_kernel<1, 8, 1, 256>, filter_mma_kernel<1, 8, 0, 256>, filter_mma_kernel<2, 8, 1, 256>,
-                          filter_mma_kernel<2, 8, 0, 256>, filter_mma_kernel<2, 8, 1, 192>, filter_mma_kernel<2, 8, 0, 192>,
-                          filter_mma_kernel<2, 8, 1, 128>, filter_mma_kernel<2, 8, 0, 128>,
-                          filter_mma_kernel<2, 16, 1, 256>, filter_mma_kernel<2, 16, 0, 256>,
-                          filter_mma_kernel<1, 8, 2, 256>, filter_mma_kernel<2, 8, 2, 256>};
+        KernelFn all[] = {filter_mma_kernel<1, 8, 0, 256, false>, filter_mma_kernel<1, 8, 1, 256, false>, filter_mma_kernel<1, 8, 2, 256, false>,
+                          filter_mma_kernel<2, 8, 0, 256, false>, filter_mma_kernel<2, 8, 1, 256, false>, filter_mma_kernel<2, 8, 2, 256, false>,
+                          filter_mma_kernel<1, 8, 0, 256, true>, filter_mma_kernel<1, 8, 1, 256, true>, filter_mma_kernel<1, 8, 2, 256, true>,
+                          filter_mma_kernel<2, 8, 0, 256, true>, filter_mma_kernel<2, 8, 1, 256, true>, filter_mma_kernel<2, 8, 2, 256, true>,
+                          filter_mma_kernel<2, 8, 1, 192, false>, filter_mma_kernel<2, 8, 0, 192, false>,
+                          filter_mma_kernel<2, 8, 1, 128, false>, filter_mma_kernel<2, 8, 0, 128, false>,
+                          filter_mma_kernel<2, 16, 1, 256, false>, filter_mma_kernel<2, 16, 0, 256, false>};
         for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
