@@ -54,6 +54,7 @@ SIGNATURES = {
     "ffr_comm_destroy": (None, [_vp]),
     "ffr_allgather_workspace_bytes": (_sz, [C.c_int, _i64]),
     "ffr_allgather_results": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "ffr_allgather_results_inplace": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
 }
 # test / tuning hooks that are not part of the public header
 HOOKS = {
@@ -61,6 +62,8 @@ HOOKS = {
     "ffr_get_recheck_delta": (_f32, []),
     "ffr_debug_set_k2_events": (None, [_vp, _vp]),
     "ffr_debug_set_prof": (None, [_vp]),
+    "ffr_debug_reload_env": (None, []),
+    "ffr_debug_last_k2_config": (None, [C.POINTER(_i32)]),
     "ffr_debug_mma_scores": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

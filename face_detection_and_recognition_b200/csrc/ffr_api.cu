@@ -2,9 +2,11 @@
 // the exact fp32 CUDA-core kernel and the tcgen05 kernel, workspace carving, the host-buffer pipeline
 // (ffr_ctx_*) and the NCCL gather (ffr_comm_*, NCCL dlopen'ed so the library loads without it).
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
 
 #include "ffr_common.cuh"
@@ -17,7 +19,9 @@ namespace ffr {
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-float g_delta = 4e-4f;       // recheck window in cosine units, see DESIGN.md §4 (fp16 operand rounding)
+std::atomic<float> g_delta{4e-4f};       // recheck window in cosine units, see DESIGN.md §4 (fp16 operand rounding)
+std::atomic<const Knobs*> g_knobs{nullptr};
+std::mutex g_knobs_mu;
 struct LastCall { const void* ws; int path; int launches; };
 thread_local LastCall g_last = {nullptr, 0, 0};
 // profiling hook: CUDA events recorded on the launch stream right before / after the tcgen05 kernel
@@ -38,17 +42,74 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int num_sms() {
-    static int cached[64] = {0};
+int current_device_slot() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
-    }
-    return cached[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
 }
+
+int num_sms() {
+    static std::atomic<int> cached[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+namespace {
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v) ? atoi(v) : dflt;
+}
+const Knobs* read_knobs() {
+    Knobs* k = new Knobs();
+    k->cta_group = env_int("FFR_CTA_GROUP", 2);
+    k->a_tmem = env_int("FFR_A_TMEM", 0);
+    k->a_stages = env_int("FFR_A_STAGES", 0);
+    k->b_stages = env_int("FFR_B_STAGES", 0);
+    k->acc_stages = env_int("FFR_ACC_STAGES", 2);
+    k->epi_warps = env_int("FFR_EPI_WARPS", 8);
+    k->diag_half_b = env_int("FFR_DIAG_HALF_B", 0);
+    k->epi_mode = env_int("FFR_EPI_MODE", 0);
+    k->discard_a = env_int("FFR_DISCARD_A", 1);
+    k->decouple_a = env_int("FFR_DECOUPLE_A", 1);
+    k->norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
+    k->norm_diag = env_int("FFR_NORM_DIAG", 0);
+    k->grid_update_refs = env_int("FFR_GRID_UPDATE_REFS", 8192);
+    k->grid_exact = env_int("FFR_GRID_EXACT", -1);
+    k->norm_ahead = env_int("FFR_NORM_AHEAD", 2);
+    k->fuse_k1 = env_int("FFR_FUSE_K1", -1);
+    k->stage32 = env_int("FFR_STAGE32", 1);
+    k->k1_blocks_per_sm = env_int("FFR_K1_BLOCKS_PER_SM", 8);
+    k->k1_subwarp = env_int("FFR_K1_SUBWARP", 1);
+    k->k1_rows = env_int("FFR_K1_ROWS", 8);
+    k->k2s_subwarp = env_int("FFR_K2S_SUBWARP", 1);
+    k->dedup_refs = env_int("FFR_DEDUP_REFS", 1);
+    k->small_n = env_int("FFR_SMALL_N", 1);
+    k->pdl = env_int("FFR_PDL", 1);
+    return k;
+}
+}  // namespace
+
+const Knobs& knobs() {
+    const Knobs* k = g_knobs.load(std::memory_order_acquire);
+    if (k == nullptr) {
+        std::lock_guard<std::mutex> lock(g_knobs_mu);
+        k = g_knobs.load(std::memory_order_acquire);
+        if (k == nullptr) { k = read_knobs(); g_knobs.store(k, std::memory_order_release); }
+    }
+    return *k;
+}
+// test hook: the previous snapshot is leaked on purpose (another thread may still hold a reference to it)
+void reload_knobs() {
+    std::lock_guard<std::mutex> lock(g_knobs_mu);
+    g_knobs.store(read_knobs(), std::memory_order_release);
+}
+float recheck_delta() { return g_delta.load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -67,7 +128,9 @@ bool mma_eligible(int64_t n_ref, int32_t dim, int metric, int flags) {
     return n_ref > 8;          // <= 8 references: the streaming fp32 kernel is already HBM-bound and exact
 }
 
-WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool mma) {
+// need_c16: the fp16 copy of the candidates lives in the workspace (false for fp16 input and for stage32, whose fp16 A
+// tiles only ever exist in shared memory: 320 MB less at BASELINE configs[4]'s shard)
+WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool mma, bool need_c16) {
     WsLayout L{};
     L.mma = mma;
     size_t off = 0;
@@ -75,7 +138,7 @@ WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool m
     if (mma) {
         const size_t ld = static_cast<size_t>(ffr_padded_dim(dim));
         L.ref16 = off;  if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_ref) * ld * 2, 256);
-        L.cand16 = off; if (dtype == FFR_DTYPE_F32) off += align_up(static_cast<size_t>(n_cand) * ld * 2, 256);
+        L.cand16 = off; if (dtype == FFR_DTYPE_F32 && need_c16) off += align_up(static_cast<size_t>(n_cand) * ld * 2, 256);
         L.recs = off;      off += align_up(static_cast<size_t>(n_cand) * sizeof(RecheckRec), 256);
         L.full_rows = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(int32_t), 256);
         L.full_keys = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(unsigned long long), 256);
@@ -109,9 +172,16 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         set_error("FFR_FLAG_FORCE_MMA: tcgen05 path needs metric cosine and dim <= 512 (dim=%d metric=%d)", dim, metric);
         return FFR_ERR_UNSUPPORTED;
     }
-    const WsLayout L = ws_layout(ref16_pre ? 0 : n_ref, n_cand, dim, dtype, mma);
+    const int32_t ld = ffr_padded_dim(dim);
+    // K2 normalises the candidates itself (K1 fused) when the shape pays for it; in its stage32 form no fp16 copy exists
+    const bool fuse = mma && dtype == FFR_DTYPE_F32 && n_cand > 0 &&
+                      filter_mma_can_fuse(static_cast<const float*>(cand), n_ref, n_cand, dim, ld);
+    const bool need_c16 = !(fuse && filter_mma_skips_cand16(n_ref, n_cand, dim));
+    const WsLayout L = ws_layout(ref16_pre ? 0 : n_ref, n_cand, dim, dtype, mma, need_c16);
     if (workspace == nullptr || ws_bytes < L.total) {
-        set_error("workspace too small: need %zu bytes, got %zu", L.total, workspace ? ws_bytes : (size_t)0);
+        set_error("workspace too small: need %zu bytes, got %zu%s", L.total, workspace ? ws_bytes : (size_t)0,
+                  (mma && dtype == FFR_DTYPE_F32 && need_c16 && (reinterpret_cast<uintptr_t>(cand) & 15) != 0)
+                      ? " (candidate rows are not 16-byte aligned: the fused schedule ffr_filter_workspace_bytes sized for cannot run)" : "");
         return FFR_ERR_WORKSPACE;
     }
     if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("workspace must be 256-byte aligned"); return FFR_ERR_INVALID; }
@@ -135,7 +205,6 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
                                   band_rows, band_cap, s);
     }
 
-    const int32_t ld = ffr_padded_dim(dim);
     const __half* ref16 = ref16_pre;
     __half* cand16 = nullptr;
     const float* fuse_cand = nullptr;        // non-null: K2 normalises the candidates itself (K1 fused)
@@ -145,12 +214,15 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         // K1: references (unless the caller cached them) and candidates in ONE launch, which also zeroes the header
         static_assert(sizeof(WsHeader) % 4 == 0 && sizeof(WsHeader) / 4 <= 256, "header is zeroed by one CTA");
         __half* r16 = ref16 == nullptr ? reinterpret_cast<__half*>(ws + L.ref16) : nullptr;
-        fuse_cand = filter_mma_can_fuse(static_cast<const float*>(cand), n_ref, n_cand, dim, ld) ? static_cast<const float*>(cand) : nullptr;
-        __half* c16 = reinterpret_cast<__half*>(ws + L.cand16);
-        const bool k1_cand = fuse_cand == nullptr;          // otherwise K2's normaliser warps write c16 themselves
-        rc = launch_l2norm_pair(k1_cand ? static_cast<const float*>(cand) : nullptr, k1_cand ? n_cand : 0, c16,
-                                r16 ? static_cast<const float*>(ref) : nullptr, r16 ? n_ref : 0, r16, dim, ld, hdr,
-                                static_cast<int32_t>(sizeof(WsHeader) / 4), s);
+        fuse_cand = fuse ? static_cast<const float*>(cand) : nullptr;
+        __half* c16 = need_c16 ? reinterpret_cast<__half*>(ws + L.cand16) : nullptr;
+        const bool k1_cand = fuse_cand == nullptr;          // otherwise K2's normaliser warps produce the fp16 rows themselves
+        const float* r32 = r16 ? static_cast<const float*>(ref) : nullptr;
+        const int64_t r_rows = r16 ? n_ref : 0;
+        if (k1_cand) rc = launch_l2norm_pair(static_cast<const float*>(cand), n_cand, c16, r32, r_rows, r16, dim, ld, hdr,
+                                             static_cast<int32_t>(sizeof(WsHeader) / 4), s);
+        else         rc = launch_l2norm_pair(r32, r_rows, r16, nullptr, 0, nullptr, dim, ld, hdr,
+                                             static_cast<int32_t>(sizeof(WsHeader) / 4), s);
         if (rc != FFR_OK) return rc;
         ++launches;
         if (r16 != nullptr) ref16 = r16;
@@ -169,12 +241,12 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     lists.full_keys = reinterpret_cast<unsigned long long*>(ws + L.full_keys);
     lists.full_ctr = reinterpret_cast<int32_t*>(ws + L.full_ctr);
     lists.full_cap = n_cand;
-    const float delta = g_delta;
+    const float delta = recheck_delta();
     float thr_band = delta;
     if (band_count != nullptr && band_tol + delta > thr_band) thr_band = band_tol + delta;
     if (g_ev_k2_begin != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_begin, s));
     rc = launch_filter_mma(ref16, n_ref, cand16, fuse_cand, dim, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
-                           best_val, lists, recheck ? 0 : 1, s);
+                           best_val, lists, recheck ? 0 : 1, band_tol, band_count, band_rows, band_cap, s);
     if (rc != FFR_OK) return rc;
     if (g_ev_k2_end != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_end, s));
     if (recheck) {
@@ -208,7 +280,9 @@ int32_t ffr_padded_dim(int32_t dim) { return (dim + 63) / 64 * 64; }
 int64_t ffr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // not in the public header: tuning / test hooks
-void ffr_set_recheck_delta(float d) { g_delta = d; }
+void ffr_set_recheck_delta(float d) { g_delta.store(d, std::memory_order_relaxed); }
+// re-read the FFR_* environment knobs (they are otherwise read once per process)
+void ffr_debug_reload_env(void) { reload_knobs(); }
 // device buffer [grid][16] u64 that the tcgen05 kernel fills with stall-cycle counters (NULL to disable)
 void ffr_debug_set_prof(void* dev_ptr) { set_mma_prof_buffer(static_cast<unsigned long long*>(dev_ptr)); }
 // cudaEvent_t pair recorded around the next tcgen05 kernel launches of this thread (NULL, NULL to disable)
@@ -216,7 +290,10 @@ void ffr_debug_set_k2_events(void* begin, void* end) {
     g_ev_k2_begin = static_cast<cudaEvent_t>(begin);
     g_ev_k2_end = static_cast<cudaEvent_t>(end);
 }
-float ffr_get_recheck_delta(void) { return g_delta; }
+float ffr_get_recheck_delta(void) { return recheck_delta(); }
+// {cta_group, grid_exact, grid_updates, normalisation mode (0 K1, 1 fused + scratch, 2 stage32), a_stages, b_stages, grid, instrumented}
+// of this thread's last tcgen05 launch
+void ffr_debug_last_k2_config(int32_t out[8]) { int v[8]; get_last_k2_config(v); for (int i = 0; i < 8; ++i) out[i] = v[i]; }
 
 int ffr_l2norm_rows_f32(const float* x, int64_t rows, int32_t dim, void* y_f16, int32_t y_f16_ld, float* y_f32,
                         float* norms, ffr_stream_t stream) {
@@ -232,7 +309,8 @@ size_t ffr_filter_workspace_bytes(int64_t n_ref, int64_t n_cand, int32_t dim, in
     if (n_ref <= 0 || n_cand < 0 || dim <= 0) return 0;
     // sized for the tcgen05 path whenever it could be chosen (including FFR_FLAG_FORCE_MMA)
     const bool mma = metric == FFR_METRIC_COSINE && dim <= 512;
-    return ws_layout(n_ref, n_cand, dim, dtype, mma).total;
+    const bool need_c16 = !(mma && dtype == FFR_DTYPE_F32 && filter_mma_skips_cand16(n_ref, n_cand, dim));
+    return ws_layout(n_ref, n_cand, dim, dtype, mma, need_c16).total;
 }
 
 int ffr_filter_ex(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype,
@@ -318,7 +396,7 @@ int ffr_debug_mma_scores(const void* ref16, int64_t n_ref, const void* cand16, i
     lists.full_ctr = reinterpret_cast<int32_t*>(ws + off);
     lists.rec_cap = lists.full_cap = n_cand;
     return launch_filter_mma_debug(static_cast<const __half*>(ref16), n_ref, static_cast<const __half*>(cand16), n_cand,
-                                   dim_pad, thr, g_delta, keep, idx, val, lists, scores, s);
+                                   dim_pad, thr, recheck_delta(), keep, idx, val, lists, scores, s);
 }
 
 }  // extern "C"
@@ -375,7 +453,7 @@ int ffr_ctx_create(int device, int64_t max_ref, int64_t chunk_cand, int32_t max_
     const size_t ld = static_cast<size_t>(ffr_padded_dim(max_dim));
     FFR_CTX_TRY(cudaMalloc(&c->d_ref, static_cast<size_t>(max_ref) * max_dim * sizeof(float)));
     FFR_CTX_TRY(cudaMalloc(&c->d_ref16, static_cast<size_t>(max_ref) * ld * 2));
-    c->ws_bytes = ffr_filter_workspace_bytes(1, chunk_cand, max_dim <= 512 ? max_dim : 512, FFR_DTYPE_F32, FFR_METRIC_COSINE);
+    c->ws_bytes = ws_layout(1, chunk_cand, max_dim <= 512 ? max_dim : 512, FFR_DTYPE_F32, true, true).total;   // any dim <= max_dim
     if (c->ws_bytes < 4096) c->ws_bytes = 4096;
     for (int i = 0; i < 2; ++i) {
         FFR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
@@ -446,6 +524,7 @@ typedef int (*pfn_init_rank)(nccl_comm_t*, int, nccl_uid, int);
 typedef int (*pfn_allgather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
 typedef int (*pfn_destroy)(nccl_comm_t);
 typedef const char* (*pfn_errstr)(int);
+typedef int (*pfn_group)(void);
 struct NcclApi {
     void* h = nullptr;
     pfn_get_uid get_uid = nullptr;
@@ -453,10 +532,13 @@ struct NcclApi {
     pfn_allgather allgather = nullptr;
     pfn_destroy destroy = nullptr;
     pfn_errstr errstr = nullptr;
+    pfn_group group_start = nullptr, group_end = nullptr;
     bool ok = false;
 } g_nccl;
+std::mutex g_nccl_mu;
 
 int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);          // (first use from several threads: dlopen + dlsym once)
     if (g_nccl.ok) return FFR_OK;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
@@ -469,7 +551,9 @@ int nccl_load() {
     g_nccl.allgather = reinterpret_cast<pfn_allgather>(dlsym(g_nccl.h, "ncclAllGather"));
     g_nccl.destroy = reinterpret_cast<pfn_destroy>(dlsym(g_nccl.h, "ncclCommDestroy"));
     g_nccl.errstr = reinterpret_cast<pfn_errstr>(dlsym(g_nccl.h, "ncclGetErrorString"));
-    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allgather || !g_nccl.destroy) {
+    g_nccl.group_start = reinterpret_cast<pfn_group>(dlsym(g_nccl.h, "ncclGroupStart"));
+    g_nccl.group_end = reinterpret_cast<pfn_group>(dlsym(g_nccl.h, "ncclGroupEnd"));
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allgather || !g_nccl.destroy || !g_nccl.group_start || !g_nccl.group_end) {
         set_error("libnccl is missing expected symbols");
         return FFR_ERR_NCCL;
     }
@@ -544,6 +628,23 @@ int ffr_allgather_results(ffr_comm* c, const uint8_t* keep_local, const int32_t*
     const int e = g_nccl.allgather(send, recv, static_cast<size_t>(m_pad) * 5, /*ncclUint8*/ 1, c->comm, s);
     if (e != 0) return nccl_fail(e, "ncclAllGather");
     return launch_unpack_results(recv, m_local, m_pad, c->nranks, keep_all, idx_all, s);
+}
+
+int ffr_allgather_results_inplace(ffr_comm* c, uint8_t* keep_all, int32_t* idx_all, int64_t m_local, ffr_stream_t stream) {
+    if (c == nullptr || keep_all == nullptr || idx_all == nullptr) { set_error("allgather_inplace: null argument"); return FFR_ERR_INVALID; }
+    if (m_local < 0) { set_error("allgather_inplace: m_local < 0"); return FFR_ERR_INVALID; }
+    if (m_local == 0) return FFR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t m = static_cast<size_t>(m_local);
+    // the two in-place gathers are fused by the group into ONE NCCL launch; this library launches no kernel of its own
+    int e = g_nccl.group_start();
+    if (e != 0) return nccl_fail(e, "ncclGroupStart");
+    e = g_nccl.allgather(idx_all + static_cast<size_t>(c->rank) * m, idx_all, m, /*ncclInt32*/ 2, c->comm, s);
+    if (e == 0) e = g_nccl.allgather(keep_all + static_cast<size_t>(c->rank) * m, keep_all, m, /*ncclUint8*/ 1, c->comm, s);
+    const int e2 = g_nccl.group_end();
+    if (e != 0) return nccl_fail(e, "ncclAllGather (in place)");
+    if (e2 != 0) return nccl_fail(e2, "ncclGroupEnd");
+    return FFR_OK;
 }
 
 }  // extern "C"

@@ -30,6 +30,20 @@ void count_launch(int n = 1);
     } while (0)
 
 int num_sms();                                             // SM count of the current device (cached)
+int current_device_slot();                                 // cudaGetDevice clamped to [0, kMaxDevices): index of per-device caches
+constexpr int kMaxDevices = 64;
+
+// ---- tuning / experiment knobs (FFR_* environment variables) -------------------------
+// Read from the environment ONCE per process (first use); the hot path never calls getenv.  Tests that flip a knob
+// between calls use the non-ABI hook ffr_debug_reload_env().  -1 = "auto" where a knob has a shape-dependent default.
+struct Knobs {
+    int cta_group, a_tmem, a_stages, b_stages, acc_stages, epi_warps, diag_half_b, epi_mode, discard_a, decouple_a,
+        norm_evict_first, norm_diag, grid_update_refs, grid_exact, norm_ahead, fuse_k1, stage32, k1_blocks_per_sm,
+        k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, small_n, pdl;
+};
+const Knobs& knobs();
+void reload_knobs();
+float recheck_delta();                                     // K3 window in cosine units; test hook can change it
 
 // ---- layout of the per-row recheck record K2 -> K3 ------------------------------------------------
 struct RecheckRec {
@@ -270,7 +284,10 @@ bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int
 int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                      RecheckLists lists, int no_recheck, cudaStream_t s);
+                      RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
+                      int64_t band_cap, cudaStream_t s);
+bool filter_mma_skips_cand16(int64_t n_ref, int64_t n_cand, int32_t dim);
+void get_last_k2_config(int out[8]);
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
                    const float* ref_norm, const float* cand_norm, float thr, int64_t ref_index_base,
                    uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,

@@ -363,7 +363,7 @@ int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64
         FFR_LAUNCH_CHECK("filter_fp32_generic");
         return FFR_OK;
     }
-    if (n_ref <= 2 && (dim == 128 || dim == 256) && !(getenv("FFR_K2S_SUBWARP") && atoi(getenv("FFR_K2S_SUBWARP")) == 0)) {
+    if (n_ref <= 2 && (dim == 128 || dim == 256) && knobs().k2s_subwarp != 0) {
         const int64_t rows_per_warp = (dim == 128 ? 4 : 2) * 2;
         const int64_t w_needed = (n_cand + rows_per_warp - 1) / rows_per_warp;
         int64_t gsub = (w_needed + (kThreads / 32) - 1) / (kThreads / 32);

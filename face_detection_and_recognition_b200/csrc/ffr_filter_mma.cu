@@ -35,6 +35,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "ffr_common.cuh"
 
 namespace ffr {
@@ -392,6 +395,10 @@ struct KParams {
     float* best_val;
     RecheckLists lists;
     int no_recheck;
+    float band_tol;                // no_recheck only: rows with |best - thr| <= band_tol are listed by the tail (with the re-check K3 lists them)
+    int32_t* band_count;
+    int64_t* band_rows;
+    int64_t band_cap;
     float* dbg_scores;
     const float* cand32;           // kNorm: original fp32 candidate rows [n_cand, dim]
     __half* cand16;                // kNorm: where the normalised fp16 rows go (leading dimension kb_count * 64)
@@ -1002,6 +1009,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
                     p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
                     if (p.best_val != nullptr) p.best_val[row] = t.b1;
+                    if (p.band_count != nullptr && fabsf(t.b1 - p.thr) <= p.band_tol) {     // (no re-check: fp16-operand score)
+                        const int32_t slot = atomicAdd(p.band_count, 1);
+                        if (p.band_rows != nullptr && slot < p.band_cap) p.band_rows[slot] = row;
+                    }
                 }
                 const bool pair = flagged && !full;
                 const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
@@ -1068,25 +1079,46 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 
 // ---- host side -----------------------------------------------------------------------------------
 
+// cuTensorMapEncodeTiled is pure host arithmetic (~1 us): a launch-bound caller (BASELINE configs[1]: ~25 us of GPU work per
+// call) repeats the same (pointer, shape) every step, so the last few encodings are kept per thread.
+struct TmapSlot { const void* base; int64_t rows; int32_t ld, box_cols, box_rows, kind; CUtensorMap map; bool valid; };
+thread_local TmapSlot g_tmaps[6];
+thread_local int g_tmap_next = 0;
+const CUtensorMap* tmap_lookup(const void* base, int64_t rows, int32_t ld, int32_t box_cols, int32_t box_rows, int kind) {
+    for (const TmapSlot& t : g_tmaps)
+        if (t.valid && t.base == base && t.rows == rows && t.ld == ld && t.box_cols == box_cols && t.box_rows == box_rows && t.kind == kind)
+            return &t.map;
+    return nullptr;
+}
+void tmap_store(const void* base, int64_t rows, int32_t ld, int32_t box_cols, int32_t box_rows, int kind, const CUtensorMap& m) {
+    TmapSlot& t = g_tmaps[g_tmap_next];
+    g_tmap_next = (g_tmap_next + 1) % 6;
+    t.base = base; t.rows = rows; t.ld = ld; t.box_cols = box_cols; t.box_rows = box_rows; t.kind = kind; t.map = m; t.valid = true;
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
+    static std::atomic<EncodeTiledFn> fn{nullptr};
+    EncodeTiledFn f = fn.load(std::memory_order_acquire);
+    if (f == nullptr) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
             q != cudaDriverEntryPointSuccess)
             return nullptr;
-        fn = reinterpret_cast<EncodeTiledFn>(p);
+        f = reinterpret_cast<EncodeTiledFn>(p);
+        fn.store(f, std::memory_order_release);
     }
-    return fn;
+    return f;
 }
 
 // fp16 matrix [rows, ld] row-major, box = [box_rows, 64 cols], 128-byte swizzle, zero fill out of bounds
 int make_tmap(CUtensorMap* m, const __half* base, int64_t rows, int32_t ld, int32_t box_rows) {
+    if (const CUtensorMap* c = tmap_lookup(base, rows, ld, kBlockK, box_rows, 16)) { *m = *c; return FFR_OK; }
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)"); return FFR_ERR_CUDA; }
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
@@ -1097,12 +1129,14 @@ int make_tmap(CUtensorMap* m, const __half* base, int64_t rows, int32_t ld, int3
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld ld=%d)", (int)r, (long long)rows, ld); return FFR_ERR_CUDA; }
+    tmap_store(base, rows, ld, kBlockK, box_rows, 16, *m);
     return FFR_OK;
 }
 
 // fp32 matrix [rows, dim] row-major (pitch dim * 4 bytes), box = [box_rows, 32 floats = 128 bytes], 128-byte swizzle, zero
 // fill out of bounds (column groups >= dim, rows past the end)
 int make_tmap_f32(CUtensorMap* m, const float* base, int64_t rows, int32_t dim, int32_t box_cols, int32_t box_rows) {
+    if (const CUtensorMap* c = tmap_lookup(base, rows, dim, box_cols, box_rows, 32)) { *m = *c; return FFR_OK; }
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)"); return FFR_ERR_CUDA; }
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
@@ -1113,33 +1147,32 @@ int make_tmap_f32(CUtensorMap* m, const float* base, int64_t rows, int32_t dim, 
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32) failed: CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim); return FFR_ERR_CUDA; }
+    tmap_store(base, rows, dim, box_cols, box_rows, 32, *m);
     return FFR_OK;
 }
 
-int env_int(const char* name, int dflt);
-
 // stage32 handles rows of 68..128 floats (dim_pad == 128; dim % 4 == 0 is already a condition of fusing)
 bool filter_mma_stage32_ok(int32_t dim, int32_t dim_pad) {
-    return dim_pad == 128 && (dim % 4) == 0 && env_int("FFR_STAGE32", 1) != 0;
+    return dim_pad == 128 && (dim % 4) == 0 && knobs().stage32 != 0;
 }
 
-unsigned long long* g_prof = nullptr;
+std::atomic<unsigned long long*> g_prof{nullptr};          // diagnostics buffer (ffr_debug_set_prof)
 
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v != nullptr && *v) ? atoi(v) : dflt;
-}
+// what the last launch of this thread looked like (test hook ffr_debug_last_k2_config)
+thread_local int g_last_cfg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 int a_stage_count(int32_t dim_pad) {
     const uint32_t a_stage = (dim_pad / kBlockK) * kABlockBytes;
     return a_stage <= 32768 ? 3 : (a_stage <= 65536 ? 2 : 1);
 }
 
+struct BandArgs { float tol; int32_t* count; int64_t* rows; int64_t cap; };
+
 // cand32 != nullptr: the candidates' normalisation runs inside the kernel, which then WRITES cand16 (workspace) itself
 int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                            int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                           RecheckLists lists, int no_recheck, float* dbg_scores, cudaStream_t s) {
+                           RecheckLists lists, int no_recheck, BandArgs band, float* dbg_scores, cudaStream_t s) {
     if (dim_pad % kBlockK != 0 || dim_pad < kBlockK || dim_pad > 512) {
         set_error("filter_mma: padded dim %d not in {64..512 step 64}", dim_pad);
         return FFR_ERR_UNSUPPORTED;
@@ -1148,11 +1181,11 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
         set_error("filter_mma: n_ref / n_cand must be < 2^31");
         return FFR_ERR_UNSUPPORTED;
     }
-    // tuning knobs (experiments only): FFR_CTA_GROUP=1|2, FFR_A_STAGES, FFR_B_STAGES
+    const Knobs& kn = knobs();                         // FFR_* experiment knobs, read once per process
     const int sms = num_sms();
     // cta_group::2 everywhere: half the B bytes per SM and 8 KB instead of 12 KB of shared-memory operand reads per MMA
     // (measured: dim 128 1292 vs 1152 TFLOP/s, dim 256 1207 vs 1010, dim 512 1429 vs 1212)
-    int cg = env_int("FFR_CTA_GROUP", 2);
+    int cg = kn.cta_group;
     if (cg != 2 || (sms & 1)) cg = 1;
     const bool fuse = cand32 != nullptr;
     const int kb = dim_pad / kBlockK;
@@ -1162,16 +1195,16 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     // N = 128 / 192 MMA with A in TMEM costs ~108 / ~144 cycles against 64 / 96 ideal, while the SS form's N = 256 MMA runs
     // at ~141 of 128 -- per 256 reference columns 6898 vs 4526 cycles at dim 512, 1539 vs 1374 at dim 128.  Off by default.
     int acc_n = kTileN;
-    if (cg == 2 && env_int("FFR_A_TMEM", 0) != 0) acc_n = dim_pad <= 256 ? 192 : 128;
+    if (cg == 2 && kn.a_tmem != 0) acc_n = dim_pad <= 256 ? 192 : 128;
     const bool ts = acc_n != kTileN;
     const uint32_t a_stage = kb * kABlockBytes;
     const uint32_t b_stage = (acc_n / cg) * kBlockK * 2;
-    int a_stages = ts ? 1 : env_int("FFR_A_STAGES", a_stage_count(dim_pad));
+    int a_stages = ts ? 1 : (kn.a_stages > 0 ? kn.a_stages : a_stage_count(dim_pad));
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
     // epilogue warps: 8 = 4 TMEM lane quadrants x 2 column parts.  FFR_EPI_WARPS=16 (SS form, cta_group::2 only) splits the
     // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
-    const int ew = (cg == 2 && env_int("FFR_EPI_WARPS", 8) == 16 && env_int("FFR_A_TMEM", 0) == 0) ? 16 : 8;
+    const int ew = (cg == 2 && kn.epi_warps == 16 && kn.a_tmem == 0) ? 16 : 8;
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
     // MMAs read the other), the B ring gets what is left (>= 2 stages)
@@ -1186,48 +1219,55 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (a_stages * a_stage + 2 * b_stage > budget) { set_error("filter_mma: not enough shared memory for dim %d", dim_pad); return FFR_ERR_UNSUPPORTED; }
     int b_stages = static_cast<int>((budget - a_stages * a_stage) / b_stage);
     if (b_stages > kMaxBStages) b_stages = kMaxBStages;
-    const int b_env = env_int("FFR_B_STAGES", 0);
-    if (b_env >= 2 && b_env < b_stages) b_stages = b_env;
+    if (kn.b_stages >= 2 && kn.b_stages < b_stages) b_stages = kn.b_stages;
     const uint32_t smem = a_stages * a_stage + b_stages * b_stage + s_bufs * kStageBytes + extra;
 
     CUtensorMap tm_c, tm_r;
     // FFR_DIAG_HALF_B=1 (timing experiments only, results are wrong): every B load fetches half its rows -- half the L2 -> SM
     // traffic with the same MMA work, to tell an L2-bandwidth bound from a latency bound
-    const int half_b = env_int("FFR_DIAG_HALF_B", 0) ? 2 : 1;
+    const int half_b = kn.diag_half_b ? 2 : 1;
     int rc = make_tmap(&tm_r, ref16, n_ref, dim_pad, acc_n / cg / half_b);
     if (rc != FFR_OK) return rc;
-    rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
-    if (rc != FFR_OK) return rc;
-    CUtensorMap tm_c32 = tm_c;                                 // (unused placeholder unless stage32)
+    if (st32) {
+        tm_c = tm_r;                                           // (unused placeholder: stage32 has no fp16 candidate matrix)
+    } else {
+        rc = make_tmap(&tm_c, cand16, n_cand, dim_pad, kTileM);
+        if (rc != FFR_OK) return rc;
+    }
+    CUtensorMap tm_c32 = tm_r;                                 // (unused placeholder unless stage32)
     if (st32) {
         rc = make_tmap_f32(&tm_c32, cand32, n_cand, dim, 32, kStageRows);
         if (rc != FFR_OK) return rc;
     }
 
+    unsigned long long* const prof = g_prof.load(std::memory_order_relaxed);
     KParams p;
     p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
     p.thr = thr; p.delta = delta; p.thr_band = thr_band; p.ref_index_base = ref_index_base;
-    p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = g_prof; p.epi_mode = env_int("FFR_EPI_MODE", 0);
-    p.acc_stages = env_int("FFR_ACC_STAGES", 2) == 1 ? 1 : 2;
+    p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = prof; p.epi_mode = kn.epi_mode;
+    p.band_tol = band.tol; p.band_count = no_recheck ? band.count : nullptr; p.band_rows = band.rows; p.band_cap = band.cap;
+    p.acc_stages = kn.acc_stages == 1 ? 1 : 2;
     p.cand32 = cand32; p.cand16 = cand16; p.dim = dim;
     p.b_tx_bytes = b_stage / half_b;
-    p.discard_a = env_int("FFR_DISCARD_A", 1);
-    p.decouple_a = env_int("FFR_DECOUPLE_A", 1);
+    p.discard_a = kn.discard_a;
+    p.decouple_a = kn.decouple_a;
     p.stage32 = st32 ? 1 : 0;
     p.s_bufs = s_bufs;
-    p.norm_evict_first = env_int("FFR_NORM_EVICT_FIRST", 1);
-    p.norm_diag = env_int("FFR_NORM_DIAG", 0);
-    p.grid_updates = n_ref <= env_int("FFR_GRID_UPDATE_REFS", 8192) ? 1 : 0;
+    p.norm_evict_first = kn.norm_evict_first;
+    p.norm_diag = kn.norm_diag;
+    p.grid_updates = n_ref <= kn.grid_update_refs ? 1 : 0;
     // The flag-only form turns every same-part near tie into a full fp32 rescan (~ near-tie fraction / parts of the rows):
     // measured a win only where the epilogue paces the kernel AND there are hundreds of parts (100 k x 128-d: 6.14 -> 5.81 ms
-    // with K3; 1 k / 4 k / 10 k references: K3 loses more than K2 gains).
-    p.grid_exact = env_int("FFR_GRID_EXACT", (dim_pad <= 128 && n_ref >= 32768) ? 0 : 1);
-    p.norm_ahead = env_int("FFR_NORM_AHEAD", 2);
-    if (p.norm_ahead < 1) p.norm_ahead = 1;
+    // with K3; 1 k / 4 k / 10 k references: K3 loses more than K2 gains).  It RELIES on K3: without the re-check (fp16 input,
+    // FFR_FLAG_NO_RECHECK, the score dump) the placeholder index it inserts would be the final answer, so those callers
+    // always get the exact per-column masks.
+    p.grid_exact = kn.grid_exact >= 0 ? kn.grid_exact : ((dim_pad <= 128 && n_ref >= 32768) ? 0 : 1);
+    if (no_recheck || dbg_scores != nullptr) p.grid_exact = 1;
+    p.norm_ahead = kn.norm_ahead < 1 ? 1 : kn.norm_ahead;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     // the instrumented instantiations exist for the default tile shape only (what tools/diag_mma.py and the tests' score dump use)
-    const bool instr = (g_prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0) && ew == 8 && acc_n == 256;
+    const bool instr = (prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0) && ew == 8 && acc_n == 256;
     KernelFn fn;
     if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, 1, 256, false> : filter_mma_kernel<2, 16, 0, 256, false>;
     else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, 1, 192, false> : filter_mma_kernel<2, 8, 0, 192, false>;
@@ -1243,21 +1283,29 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
         set_error("filter_mma: score dump / epilogue diagnostics need the default tile shape (FFR_EPI_WARPS=8, FFR_A_TMEM=0)");
         return FFR_ERR_UNSUPPORTED;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        KernelFn all[] = {filter_mma_kernel<1, 8, 0, 256, false>, filter_mma_kernel<1, 8, 1, 256, false>, filter_mma_kernel<1, 8, 2, 256, false>,
-                          filter_mma_kernel<2, 8, 0, 256, false>, filter_mma_kernel<2, 8, 1, 256, false>, filter_mma_kernel<2, 8, 2, 256, false>,
-                          filter_mma_kernel<1, 8, 0, 256, true>, filter_mma_kernel<1, 8, 1, 256, true>, filter_mma_kernel<1, 8, 2, 256, true>,
-                          filter_mma_kernel<2, 8, 0, 256, true>, filter_mma_kernel<2, 8, 1, 256, true>, filter_mma_kernel<2, 8, 2, 256, true>,
-                          filter_mma_kernel<2, 8, 1, 192, false>, filter_mma_kernel<2, 8, 0, 192, false>,
-                          filter_mma_kernel<2, 8, 1, 128, false>, filter_mma_kernel<2, 8, 0, 128, false>,
-                          filter_mma_kernel<2, 16, 1, 256, false>, filter_mma_kernel<2, 16, 0, 256, false>};
-        for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        attr_set = true;
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: set once per device this process uses
+    {
+        static std::mutex mu;
+        static bool attr_set[kMaxDevices] = {};
+        const int slot = current_device_slot();
+        std::lock_guard<std::mutex> lock(mu);
+        if (!attr_set[slot]) {
+            KernelFn all[] = {filter_mma_kernel<1, 8, 0, 256, false>, filter_mma_kernel<1, 8, 1, 256, false>, filter_mma_kernel<1, 8, 2, 256, false>,
+                              filter_mma_kernel<2, 8, 0, 256, false>, filter_mma_kernel<2, 8, 1, 256, false>, filter_mma_kernel<2, 8, 2, 256, false>,
+                              filter_mma_kernel<1, 8, 0, 256, true>, filter_mma_kernel<1, 8, 1, 256, true>, filter_mma_kernel<1, 8, 2, 256, true>,
+                              filter_mma_kernel<2, 8, 0, 256, true>, filter_mma_kernel<2, 8, 1, 256, true>, filter_mma_kernel<2, 8, 2, 256, true>,
+                              filter_mma_kernel<2, 8, 1, 192, false>, filter_mma_kernel<2, 8, 0, 192, false>,
+                              filter_mma_kernel<2, 8, 1, 128, false>, filter_mma_kernel<2, 8, 0, 128, false>,
+                              filter_mma_kernel<2, 16, 1, 256, false>, filter_mma_kernel<2, 16, 0, 256, false>};
+            for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            attr_set[slot] = true;
+        }
     }
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);
     const int64_t max_groups = sms / cg;
     const unsigned grid = static_cast<unsigned>((n_tiles < max_groups ? n_tiles : max_groups) * cg);
+    g_last_cfg[0] = cg; g_last_cfg[1] = p.grid_exact; g_last_cfg[2] = p.grid_updates; g_last_cfg[3] = st32 ? 2 : (fuse ? 1 : 0);
+    g_last_cfg[4] = a_stages; g_last_cfg[5] = b_stages; g_last_cfg[6] = static_cast<int>(grid); g_last_cfg[7] = instr ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(64 + 32 * ew + (fuse ? 64 : 0));
@@ -1281,7 +1329,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
 // separate full-bandwidth K1 pass is the better schedule.  FFR_FUSE_K1=0|1 forces the choice (tests).
 bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int32_t dim, int32_t dim_pad) {
     if (cand32 == nullptr || (dim % 4) != 0 || (reinterpret_cast<uintptr_t>(cand32) & 15) != 0) return false;
-    const int forced = env_int("FFR_FUSE_K1", -1);
+    const int forced = knobs().fuse_k1;
     if (forced >= 0) return forced != 0;
     // Tensor time per candidate tile ~ n_rt * (dim_pad / 64) * 512 cycles; the two normaliser warps keep <= 16 KB in flight per
     // SM (~7 B/cycle against HBM latency), i.e. ~75 * dim cycles per 128-row tile: hidden with 2x margin from ~20 reference
@@ -1289,7 +1337,7 @@ bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int
     const int64_t n_rt = (n_ref + kTileN - 1) / kTileN;
     // stage32 (128-d rows): the fp32 rows come through a TMA-fed shared-memory ring, two warps convert a tile in ~4 k cycles
     // -- hidden behind even ONE reference tile's epilogue -- so the K1 pass over the candidates goes whatever n_ref is
-    if (filter_mma_stage32_ok(dim, dim_pad) && env_int("FFR_CTA_GROUP", 2) == 2)
+    if (filter_mma_stage32_ok(dim, dim_pad) && knobs().cta_group == 2)
         return n_cand >= 4 * static_cast<int64_t>(kTileM) * num_sms();
     return n_rt >= 24 && n_cand >= 4 * static_cast<int64_t>(kTileM) * num_sms();
 }
@@ -1297,19 +1345,32 @@ bool filter_mma_can_fuse(const float* cand32, int64_t n_ref, int64_t n_cand, int
 int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                      RecheckLists lists, int no_recheck, cudaStream_t s) {
+                      RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
+                      int64_t band_cap, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, cand16, cand32, dim, n_cand, dim_pad, thr, delta, thr_band, ref_index_base,
-                                  keep, idx, val, lists, no_recheck, nullptr, s);
+                                  keep, idx, val, lists, no_recheck, BandArgs{band_tol, band_count, band_rows, band_cap}, nullptr, s);
 }
 
-void set_mma_prof_buffer(unsigned long long* dev_ptr) { g_prof = dev_ptr; }
+// true when the fused schedule needs NO fp16 copy of the candidates in the workspace (stage32: the fp16 A tiles only ever
+// exist in shared memory), decided from the shape alone -- ffr_filter_workspace_bytes sizes the workspace with it.  The
+// candidate pointer is assumed 16-byte aligned (the header's contract); a misaligned one is rejected by ffr_filter.
+bool filter_mma_skips_cand16(int64_t n_ref, int64_t n_cand, int32_t dim) {
+    const int32_t dim_pad = (dim + 63) / 64 * 64;
+    const Knobs& kn = knobs();
+    if (kn.cta_group != 2 || (num_sms() & 1) || kn.a_tmem != 0 || kn.epi_warps == 16) return false;
+    if (!filter_mma_stage32_ok(dim, dim_pad)) return false;
+    return filter_mma_can_fuse(reinterpret_cast<const float*>(uintptr_t(256)), n_ref, n_cand, dim, dim_pad);
+}
+
+void set_mma_prof_buffer(unsigned long long* dev_ptr) { g_prof.store(dev_ptr, std::memory_order_relaxed); }
+void get_last_k2_config(int out[8]) { for (int i = 0; i < 8; ++i) out[i] = g_last_cfg[i]; }
 
 // test hook (not part of the ABI in include/ffr.h): additionally dumps the full score matrix
 int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* cand16, int64_t n_cand, int32_t dim_pad,
                             float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                             float* scores, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, const_cast<__half*>(cand16), nullptr, dim_pad, n_cand, dim_pad, thr, delta, delta, 0, keep, idx,
-                                  val, lists, 0, scores, s);
+                                  val, lists, 0, BandArgs{0.f, nullptr, nullptr, 0}, scores, s);
 }
 
 }  // namespace ffr

@@ -8,6 +8,8 @@
 // on the ORIGINAL fp32 embeddings: only the two leading references when the third-best score was clearly
 // lower, the whole reference set otherwise (first-occurrence argmax, strict '>' in ascending order).
 // One warp per flagged row; the candidate row is parked in shared memory.
+#include <mutex>
+
 #include "ffr_common.cuh"
 
 namespace ffr {
@@ -513,10 +515,15 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     const int64_t gx = static_cast<int64_t>(sms) * 2;         // two blocks per SM are resident (registers): one wave
     const dim3 g2(static_cast<unsigned>(gx));
     const size_t smem_full = smem + static_cast<size_t>(kTileRefs) * kKCPad * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
+    {   // per-DEVICE function attribute: once for every device this process uses
+        static std::mutex mu;
+        static bool attr_set[kMaxDevices] = {};
+        const int slot = current_device_slot();
+        std::lock_guard<std::mutex> lock(mu);
+        if (!attr_set[slot]) {
+            FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[slot] = true;
+        }
     }
     if (vec) recheck_kernel<true><<<g2, kThreads, smem_full, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
                                                               lists, band_tol, band_count, band_rows, band_cap);

@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import (DTYPE_F16, DTYPE_F32, FLAG_FORCE_FP32, FLAG_FORCE_MMA, FLAG_NO_RECHECK, METRIC_COSINE,
                    METRIC_EUCLID, check)
 
-__all__ = ["l2norm_rows", "face_filter", "cosine_filter", "ref_mean_and_thres", "FilterResult", "HostFilter",
+__all__ = ["l2norm_rows", "face_filter", "cosine_filter", "ref_mean_and_thres", "FilterResult", "HostFilter", "GraphedFilter",
            "ResultGather", "launch_count", "METRIC_COSINE", "METRIC_EUCLID", "FLAG_FORCE_FP32", "FLAG_FORCE_MMA",
            "FLAG_NO_RECHECK"]
 
@@ -154,33 +154,56 @@ def face_filter(ref: torch.Tensor, cand: torch.Tensor, thr: float, metric="cosin
             check(lib.ffr_filter_stats(ws.data_ptr(), arr, _stream_ptr(dev)))
             res.stats = {"rechecked": arr[0], "full_rescans": arr[1], "path": "tcgen05" if arr[2] == 1 else "fp32",
                          "launches": arr[3]}
+            if arr[2] == 1:
+                cfg = (C.c_int32 * 8)()
+                lib.ffr_debug_last_k2_config(cfg)
+                res.stats["k2"] = {"cta_group": cfg[0], "grid_exact": cfg[1], "grid_updates": cfg[2],
+                                   "normalise": ("k1", "fused_scratch", "stage32")[cfg[3]], "a_stages": cfg[4],
+                                   "b_stages": cfg[5], "grid": cfg[6]}
     return res
 
 
 class GraphedFilter:
-    """``face_filter`` for fixed shapes captured once into a CUDA graph: the whole K1 -> K2 -> K3 launch sequence
-    (two memsets + five kernels) replays as ONE graph launch.  Worth it when the step is launch-bound (BASELINE
-    configs[1]: ~100 us of GPU work).  Inputs are copied into / results read from the static tensors ``ref``, ``cand``,
-    ``result``."""
+    """``face_filter`` for fixed shapes captured once into a CUDA graph: the whole K1 -> K2 -> K3 launch sequence replays
+    as ONE graph launch with no host work between the kernels.  Worth it when the step is launch-bound (BASELINE
+    configs[1]: ~25 us of GPU work).  Either own static input tensors (``GraphedFilter(n_ref, n_cand, dim, thr)``; inputs
+    are copied in by ``__call__``) or wrap the caller's tensors in place (``GraphedFilter.capture(ref, cand, thr, out=...)``:
+    ``replay()`` re-runs the filter on whatever those tensors hold)."""
 
-    def __init__(self, n_ref: int, n_cand: int, dim: int, thr: float, metric="cosine", device: int = 0, flags: int = 0):
+    def __init__(self, n_ref: int, n_cand: int, dim: int, thr: float, metric="cosine", device: int = 0, flags: int = 0,
+                 _tensors=None):
         self.dev = torch.device("cuda", device)
-        self.ref = torch.zeros((n_ref, dim), dtype=torch.float32, device=self.dev)
-        self.cand = torch.zeros((n_cand, dim), dtype=torch.float32, device=self.dev)
         self.thr, self.metric, self.flags = float(thr), metric, flags
-        out = (torch.empty(n_cand, dtype=torch.uint8, device=self.dev), torch.empty(n_cand, dtype=torch.int32, device=self.dev),
-               torch.empty(n_cand, dtype=torch.float32, device=self.dev))
-        self.ref.normal_()
-        self.cand.normal_()
+        if _tensors is None:
+            self.ref = torch.zeros((n_ref, dim), dtype=torch.float32, device=self.dev)
+            self.cand = torch.zeros((n_cand, dim), dtype=torch.float32, device=self.dev)
+            out = (torch.empty(n_cand, dtype=torch.uint8, device=self.dev), torch.empty(n_cand, dtype=torch.int32, device=self.dev),
+                   torch.empty(n_cand, dtype=torch.float32, device=self.dev))
+            self.ref.normal_()
+            self.cand.normal_()
+        else:
+            self.ref, self.cand, out = _tensors
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):                              # warm-up on the side stream (workspace, attributes)
+            l0 = launch_count()
             face_filter(self.ref, self.cand, self.thr, metric=metric, flags=flags, out=out)
+            self.launches = launch_count() - l0                    # kernels of this library per replay
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
             self.result = face_filter(self.ref, self.cand, self.thr, metric=metric, flags=flags, out=out)
+
+    @classmethod
+    def capture(cls, ref: torch.Tensor, cand: torch.Tensor, thr: float, metric="cosine", flags: int = 0, out=None):
+        ref, cand = _require_cuda(ref, "ref"), _require_cuda(cand, "cand")
+        if out is None:
+            out = (torch.empty(cand.shape[0], dtype=torch.uint8, device=cand.device),
+                   torch.empty(cand.shape[0], dtype=torch.int32, device=cand.device),
+                   torch.empty(cand.shape[0], dtype=torch.float32, device=cand.device))
+        return cls(ref.shape[0], cand.shape[0], ref.shape[1], thr, metric=metric, device=cand.device.index, flags=flags,
+                   _tensors=(ref, cand, out))
 
     def replay(self) -> FilterResult:
         self.graph.replay()
@@ -349,6 +372,26 @@ class ResultGather:
         if getattr(self, "_h", None):
             self._lib.ffr_comm_destroy(self._h)
             self._h = C.c_void_p()
+
+    def buffers(self, m_local: int, device=None):
+        """In-place form: returns (keep_all, idx_all, keep_mine, idx_mine).  Hand ``keep_mine`` / ``idx_mine`` (views of
+        this rank's slice) to ``face_filter(out=...)`` and call ``all_gather_inplace`` -- no pack / unpack kernels."""
+        dev = torch.device("cuda", self.device) if device is None else device
+        key = (m_local, dev)
+        if getattr(self, "_buf_key", None) != key:
+            self._keep_all = torch.empty((m_local * self.world_size,), dtype=torch.uint8, device=dev)
+            self._idx_all = torch.empty((m_local * self.world_size,), dtype=torch.int32, device=dev)
+            self._buf_key = key
+        a, b = self.rank * m_local, (self.rank + 1) * m_local
+        return self._keep_all, self._idx_all, self._keep_all[a:b], self._idx_all[a:b]
+
+    def all_gather_inplace(self, keep_all: torch.Tensor, idx_all: torch.Tensor):
+        m = keep_all.numel() // self.world_size
+        dev = keep_all.device
+        with torch.cuda.device(dev):
+            check(self._lib.ffr_allgather_results_inplace(self._h, keep_all.data_ptr(), idx_all.data_ptr(), m,
+                                                          _stream_ptr(dev)))
+        return keep_all, idx_all
 
     def all_gather(self, keep_local: torch.Tensor, idx_local: torch.Tensor):
         m = keep_local.numel()

@@ -8,7 +8,8 @@ ranks exists on this path; nothing else crosses NVLink.
 
 Two gather back ends share one wire format ([idx i32 x m_pad][keep u8 x m_pad] per rank, m_pad = m_local rounded up
 to 16):
-  * ``"nccl"``  libffr_b200.so's own communicator (ffr_comm_*, K4 pack -> ncclAllGather -> unpack), used on GPUs;
+  * ``"nccl"``  libffr_b200.so's own communicator (ffr_comm_*, K4: every rank's filter writes its slice of the final
+    arrays, one grouped in-place ncclAllGather fills in the others), used on GPUs;
   * ``"dist"``  ``torch.distributed.all_gather_into_tensor`` on the process group the caller initialised -- this is
     what the world_size-2 ``gloo`` tests exercise on CPU (host-side plumbing only; the filter itself is injected).
 """
@@ -89,11 +90,13 @@ class CandidateSharder:
         if self.world == 1:
             return res.keep, res.best_idx, res
         if self.gather == "nccl":
+            # in-place gather: this rank's slice of the final arrays is filled, one grouped NCCL launch fills the rest
+            # (callers that own the output buffers skip even this copy: ResultGather.buffers + face_filter(out=...))
             n = res.keep.numel()
-            keep_l = torch.zeros(m_local, dtype=torch.uint8, device=res.keep.device)
-            idx_l = torch.zeros(m_local, dtype=torch.int32, device=res.keep.device)
-            keep_l[:n], idx_l[:n] = res.keep, res.best_idx
-            keep_all, idx_all = self._rg.all_gather(keep_l, idx_l)
+            keep_all, idx_all, keep_mine, idx_mine = self._rg.buffers(m_local, res.keep.device)
+            keep_mine[:n], idx_mine[:n] = res.keep, res.best_idx
+            keep_mine[n:], idx_mine[n:] = 0, 0
+            self._rg.all_gather_inplace(keep_all, idx_all)
             return keep_all[:n_cand_total], idx_all[:n_cand_total], res
         import torch.distributed as dist
         send = pack_results(res.keep, res.best_idx, m_local)

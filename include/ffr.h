@@ -154,6 +154,11 @@ size_t ffr_allgather_workspace_bytes(int nranks, int64_t m_local);
 int  ffr_allgather_results(ffr_comm* comm, const uint8_t* keep_local, const int32_t* idx_local, int64_t m_local,
                            uint8_t* keep_all, int32_t* idx_all, void* workspace, size_t ws_bytes,
                            ffr_stream_t stream);
+/* In-place form (no pack / unpack kernels, no workspace): this rank's ffr_filter already wrote its m_local results at
+ * keep_all + rank * m_local and idx_all + rank * m_local (pass those as the filter's keep / best_idx outputs); the two
+ * in-place ncclAllGather calls are grouped into ONE NCCL launch that fills in everybody else's slices. */
+int  ffr_allgather_results_inplace(ffr_comm* comm, uint8_t* keep_all, int32_t* idx_all, int64_t m_local,
+                                   ffr_stream_t stream);
 
 #ifdef __cplusplus
 }

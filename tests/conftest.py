@@ -33,3 +33,37 @@ def cuda_dev():
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+class _FfrEnv:
+    """FFR_* experiment knobs are read ONCE per process by libffr_b200.so; tests that flip one between calls go through
+    this helper, which also asks the library to re-read its environment (non-ABI hook ffr_debug_reload_env)."""
+
+    def __init__(self, lib):
+        self._lib, self._old = lib, {}
+
+    def setenv(self, key, value):
+        self._old.setdefault(key, os.environ.get(key))
+        os.environ[key] = str(value)
+        self._lib.ffr_debug_reload_env()
+
+    def delenv(self, key):
+        self._old.setdefault(key, os.environ.get(key))
+        os.environ.pop(key, None)
+        self._lib.ffr_debug_reload_env()
+
+    def restore(self):
+        for k, v in self._old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        self._old.clear()
+        self._lib.ffr_debug_reload_env()
+
+
+@pytest.fixture
+def ffr_env(ffr_lib):
+    e = _FfrEnv(ffr_lib)
+    yield e
+    e.restore()

@@ -35,9 +35,13 @@ def test_padded_dim_and_workspace_queries(ffr_lib):
     assert [ffr_lib.ffr_padded_dim(d) for d in (1, 64, 65, 128, 200, 512)] == [64, 64, 128, 128, 256, 512]
     assert ffr_lib.ffr_filter_workspace_bytes(0, 10, 128, 0, 0) == 0
     small = ffr_lib.ffr_filter_workspace_bytes(1, 1000, 128, 0, 1)          # euclid -> fp32 path, header only
-    big = ffr_lib.ffr_filter_workspace_bytes(1000, 100000, 128, 0, 0)       # cosine -> fp16 copies + recheck list
+    big = ffr_lib.ffr_filter_workspace_bytes(1000, 100000, 256, 0, 0)       # cosine -> fp16 copies + recheck list
     assert small == 256
-    assert big >= 1000 * 128 * 2 + 100000 * 128 * 2 + 100000 * 16
+    assert big >= 1000 * 256 * 2 + 100000 * 256 * 2 + 100000 * 16
+    # 128-d rows at this size take the stage32 schedule: the fp16 A tiles only exist in shared memory, no fp16 copy of the
+    # candidates in the workspace (references + re-check lists only)
+    st32 = ffr_lib.ffr_filter_workspace_bytes(1000, 100000, 128, 0, 0)
+    assert 1000 * 128 * 2 + 100000 * 28 <= st32 < 1000 * 128 * 2 + 100000 * 28 + 100000 * 128 * 2
     assert ffr_lib.ffr_allgather_workspace_bytes(8, 1000) >= 9 * 1008 * 5
 
 

@@ -25,25 +25,39 @@ def ops(ffr_lib, cuda_dev):
     return _ops
 
 
-def _top2_gap64(ref, cand):
+def _top2_gap64(ref, cand, block=512):
+    """fp64 shadow: (gap between the two leading scores, best score) per candidate, blocked over the candidates so that
+    100 k references stay within a few hundred MB."""
     r = ref.astype(np.float64)
-    c = cand.astype(np.float64)
     r /= np.linalg.norm(r, axis=1, keepdims=True)
-    c /= np.linalg.norm(c, axis=1, keepdims=True)
-    s = r @ c.T
-    if s.shape[0] == 1:
-        return np.full(s.shape[1], np.inf), s[0]
-    part = np.partition(s, -2, axis=0)
-    return part[-1] - part[-2], part[-1]
+    gap = np.empty(len(cand))
+    best = np.empty(len(cand))
+    for s0 in range(0, len(cand), block):
+        c = cand[s0:s0 + block].astype(np.float64)
+        c /= np.linalg.norm(c, axis=1, keepdims=True)
+        s = r @ c.T
+        if s.shape[0] == 1:
+            gap[s0:s0 + block], best[s0:s0 + block] = np.inf, s[0]
+            continue
+        b1 = s.max(axis=0)
+        a1 = s.argmax(axis=0)
+        s[a1, np.arange(s.shape[1])] = -np.inf
+        gap[s0:s0 + block], best[s0:s0 + block] = b1 - s.max(axis=0), b1
+    return gap, best
 
 
-def _check_cosine(ops, ref, cand, thr, flags=0, band_tol=1e-3):
+def _check_cosine(ops, ref, cand, thr, flags=0, band_tol=1e-3, sample=None):
+    """GPU filter over ALL candidates against the oracle (+ fp64 shadow); ``sample`` = row subset the oracle is run on (the
+    band listing is then checked on that subset)."""
     dev = torch.device("cuda:0")
     res = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev), thr, metric="cosine",
                           band_tol=band_tol, flags=flags, want_stats=True)
     torch.cuda.synchronize()
     keep, idx, val = res.keep.cpu().numpy(), res.best_idx.cpu().numpy(), res.best_val.cpu().numpy()
-    ko, io, so = oracle.filter_cosine(ref, cand, thr)
+    if sample is not None:
+        sample = np.sort(np.asarray(sample))
+        keep, idx, val, cand = keep[sample], idx[sample], val[sample], cand[sample]
+    ko, io, so = oracle.filter_cosine(ref, cand, thr, block=1024 if len(ref) > 20_000 else 8192)
     gap, best64 = _top2_gap64(ref, cand)
     assert np.max(np.abs(val - so)) <= VAL_TOL, f"max |sim - oracle| = {np.max(np.abs(val - so))}"
     unamb = gap > TIE_EPS
@@ -58,6 +72,9 @@ def _check_cosine(ops, ref, cand, thr, flags=0, band_tol=1e-3):
     # the listed band must contain every row whose fp64 best is within band_tol - noise of thr
     if band_tol is not None:
         listed = set(res.band_rows.cpu().numpy().tolist())
+        if sample is not None:
+            pos = {int(r): i for i, r in enumerate(sample)}
+            listed = {pos[r] for r in listed if r in pos}
         must = set(np.flatnonzero(np.abs(best64 - thr) <= band_tol - 1e-5).tolist())
         may = set(np.flatnonzero(np.abs(best64 - thr) <= band_tol + 1e-5).tolist())
         assert must <= listed <= may, (len(must - listed), len(listed - may))
@@ -230,16 +247,16 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
                                               (300, 60_000, 128), (700, 45_000, 512), (257, 40_001, 320),
                                               (90, 38_000 + 100, 260), (33, 19_000 + 129, 64), (64, 512 * 74 + 77, 128),
                                               (500, 40_000, 100), (1100, 20_001, 72), (260, 57_000, 124)])
-def test_fused_normalisation_path(ops, monkeypatch, n_ref, n_cand, dim):
+def test_fused_normalisation_path(ops, ffr_env, n_ref, n_cand, dim):
     """K2 with in-kernel normalisation of the candidates (two normaliser warps write the fp16 rows of the CTA's next tile
     into the workspace while the tensor core works; default for large reference sets, forced here with FFR_FUSE_K1=1):
     same parity bar as K1 + K2, and the same decisions as the K1 + K2 schedule.  Rows of 68..128 floats take the stage32
     form (fp32 rows staged through shared memory by TMA, fp16 A tile written in place, no global scratch)."""
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=dim + n_ref, n_adversarial=100, n_dup_refs=8, unit_norm=False)
-    monkeypatch.setenv("FFR_FUSE_K1", "1")
+    ffr_env.setenv("FFR_FUSE_K1", "1")
     res = _check_cosine(ops, ref, cand, 0.5)
     assert res.stats["launches"] == 3                      # K1(references only) + K2 + K3: no K1 pass over the candidates
-    monkeypatch.setenv("FFR_FUSE_K1", "0")
+    ffr_env.setenv("FFR_FUSE_K1", "0")
     import torch
     r2 = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, band_tol=1e-3)
     # the two schedules differ by <= 1 fp16 ulp in rare operand elements (x * (1/|x|) vs x / |x|): same decisions
@@ -303,10 +320,10 @@ def test_errors_are_loud(ffr_lib, ops):
 
 
 @pytest.mark.parametrize("n_ref,n_cand,dim", [(700, 3000, 128), (513, 2500, 256), (1000, 2049, 512), (300, 40_000, 384)])
-def test_a_operand_in_tensor_memory_variant(ops, monkeypatch, n_ref, n_cand, dim):
+def test_a_operand_in_tensor_memory_variant(ops, ffr_env, n_ref, n_cand, dim):
     """K2 with the A tile in tensor memory (tcgen05.cp from a staging tile, tcgen05.mma with a TMEM A operand, 192- or
     128-column accumulator stages; FFR_A_TMEM=1, off by default because it measured slower): same parity bar."""
-    monkeypatch.setenv("FFR_A_TMEM", "1")
+    ffr_env.setenv("FFR_A_TMEM", "1")
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=3 * dim + n_ref, n_adversarial=100, n_dup_refs=8)
     _check_cosine(ops, ref, cand, 0.5)
 
@@ -336,14 +353,14 @@ def _near_tie_refs(n_ref, dim, seed, n_pairs):
 
 @pytest.mark.parametrize("n_ref,n_cand,dim", [(700, 6000, 128), (1500, 3000, 256), (9000, 2500, 128), (300, 40_000, 64)])
 @pytest.mark.parametrize("mode", ["default", "flag_only", "gated"])
-def test_update_grid_variants(ops, monkeypatch, n_ref, n_cand, dim, mode):
+def test_update_grid_variants(ops, ffr_env, n_ref, n_cand, dim, mode):
     """update_grid (unconditional / gated), its two fall-backs for several in-window columns in one part (exact per-column
     masks, or flag-the-row-for-the-full-rescan) all meet the same parity bar -- on references with planted near-duplicates,
     so that the fall-backs actually run."""
     env = {"default": {}, "flag_only": {"FFR_GRID_EXACT": "0"},
            "gated": {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "1"}}[mode]
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
+        ffr_env.setenv(k, v)
     ref = _near_tie_refs(n_ref, dim, seed=n_ref + dim, n_pairs=40)
     rng = np.random.default_rng(n_cand)
     cand = rng.standard_normal((n_cand, dim)).astype(np.float32)
@@ -355,7 +372,7 @@ def test_update_grid_variants(ops, monkeypatch, n_ref, n_cand, dim, mode):
     assert res.stats["rechecked"] + res.stats["full_rescans"] > 0
 
 
-def test_update_grid_variants_agree_bitwise(ops, monkeypatch):
+def test_update_grid_variants_agree_bitwise(ops, ffr_env):
     """Every epilogue variant hands K3 what it needs: after the fp32 re-check the outputs are IDENTICAL, bit for bit."""
     ref = _near_tie_refs(2000, 128, seed=11, n_pairs=60)
     rng = np.random.default_rng(12)
@@ -366,12 +383,12 @@ def test_update_grid_variants_agree_bitwise(ops, monkeypatch):
     outs = []
     for env in ({}, {"FFR_GRID_EXACT": "0"}, {"FFR_GRID_UPDATE_REFS": "0"}, {"FFR_GRID_UPDATE_REFS": "0", "FFR_GRID_EXACT": "0"},
                 {"FFR_CTA_GROUP": "1"}):
-        with monkeypatch.context() as m:
-            for k, v in env.items():
-                m.setenv(k, v)
-            res = ops.face_filter(r_t, c_t, 0.5, want_stats=True)
-            torch.cuda.synchronize()
-            outs.append((res.keep.cpu().numpy().copy(), res.best_idx.cpu().numpy().copy(), res.best_val.cpu().numpy().copy()))
+        for k, v in env.items():
+            ffr_env.setenv(k, v)
+        res = ops.face_filter(r_t, c_t, 0.5, want_stats=True)
+        torch.cuda.synchronize()
+        outs.append((res.keep.cpu().numpy().copy(), res.best_idx.cpu().numpy().copy(), res.best_val.cpu().numpy().copy()))
+        ffr_env.restore()
     gap, _ = _top2_gap64(ref, cand)
     unamb = gap > TIE_EPS
     for k, i, v in outs[1:]:
@@ -392,14 +409,94 @@ def test_candidate_tile_sequences(ops, tiles_per_cta, dim, n_ref):
 
 
 @pytest.mark.parametrize("stage32", ["1", "0"])
-def test_fused_forms_agree(ops, monkeypatch, stage32):
+def test_fused_forms_agree(ops, ffr_env, stage32):
     """stage32 and the global-scratch form of the in-kernel normalisation do the same arithmetic per row (one float4 per
     lane, warp-shuffle sum, one division, multiplies): identical fp16 operands, hence identical outputs as the direct form
     with FFR_STAGE32=0.  Also covers cta_group::1 (five staging buffers instead of six)."""
     ref, cand = oracle.make_synthetic(900, 128 * 148 * 2 + 55, 128, seed=3, n_adversarial=200, n_dup_refs=16, unit_norm=False)
-    monkeypatch.setenv("FFR_FUSE_K1", "1")
-    monkeypatch.setenv("FFR_STAGE32", stage32)
+    ffr_env.setenv("FFR_FUSE_K1", "1")
+    ffr_env.setenv("FFR_STAGE32", stage32)
     res = _check_cosine(ops, ref, cand, 0.5)
-    monkeypatch.setenv("FFR_CTA_GROUP", "1")
+    ffr_env.setenv("FFR_CTA_GROUP", "1")
     r1 = _check_cosine(ops, ref, cand, 0.5)
     assert torch.equal(res.keep, r1.keep) and torch.equal(res.best_idx, r1.best_idx)
+
+
+# ---------------------------------------------------------------- BASELINE configs[4]'s own reference count (round 2)
+def _large_gallery(n_ref, n_cand, dim, seed):
+    """100 k-reference gallery with the hard rows planted: near-duplicate references inside one 128-column part and
+    across parts / tiles, exact duplicates, candidates within +-2e-3 of the threshold, and candidates sitting on the
+    near-duplicate pairs (so the near ties are actually leading)."""
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=seed, n_adversarial=1000, n_dup_refs=1000)
+    rng = np.random.default_rng(seed + 1)
+    offs = (3, 9, 40, 130, 300, 70_000)
+    src = rng.integers(0, n_ref // 4, 600)
+    for k, i in enumerate(src):
+        j = int(i) + offs[k % len(offs)]
+        ref[j] = ref[i] + rng.standard_normal(dim).astype(np.float32) * 0.0004      # cos ~ 1 - 1e-5: inside delta
+        ref[j] /= np.linalg.norm(ref[j])
+    rows = rng.choice(n_cand, 3000, replace=False)
+    tgt = src[rng.integers(0, len(src), len(rows))]
+    noise = rng.standard_normal((len(rows), dim)).astype(np.float32)
+    noise /= np.linalg.norm(noise, axis=1, keepdims=True)
+    cand[rows] = 0.8 * ref[tgt] + 0.6 * noise
+    return ref, cand, rows
+
+
+def test_filter_mma_config4_gallery_size(ops):
+    """n_ref = 100 000 x 128-d, default knobs: 391 reference tiles per candidate tile, indices > 65 535, the gated
+    update_grid with the FLAG-ONLY fall-back (grid_exact = 0) and K3's full rescan over 100 k rows; >= 2 candidate tiles
+    per CTA.  Oracle (fp32 + fp64 shadow) on a 3 k-row sample that contains every planted near-tie row."""
+    n_ref, n_cand, dim = 100_000, 40_000, 128
+    ref, cand, hard = _large_gallery(n_ref, n_cand, dim, seed=4)
+    rng = np.random.default_rng(0)
+    sample = np.unique(np.concatenate([hard[:1500], rng.choice(n_cand, 1500, replace=False)]))
+    res = _check_cosine(ops, ref, cand, 0.5, sample=sample)
+    assert res.stats["path"] == "tcgen05"
+    assert res.stats["k2"]["grid_exact"] == 0 and res.stats["k2"]["grid_updates"] == 0, res.stats
+    assert res.stats["full_rescans"] > 0 and res.stats["rechecked"] > 0
+    assert int(res.best_idx.max()) > 65_535
+
+
+def test_filter_mma_large_gallery_without_recheck_is_exact_in_fp16_space(ops, ffr_env):
+    """fp16 input / FFR_FLAG_NO_RECHECK have no K3 behind them: the flag-only fall-back (placeholder column + 'rescan
+    me') must not be taken, whatever FFR_GRID_EXACT says.  Every returned index must carry the row's best fp16-space
+    score (ties -> first), also on rows with several in-window columns in one 128-column part."""
+    from face_detection_and_recognition_b200.ops import FLAG_NO_RECHECK
+    n_ref, n_cand, dim = 40_000, 6_000, 128
+    ref, cand, hard = _large_gallery(n_ref, n_cand, dim, seed=9)
+    ffr_env.setenv("FFR_GRID_EXACT", "0")
+    r16 = ops.l2norm_rows(torch.from_numpy(ref).cuda(), want_f16=True, want_f32=False)["f16"]
+    c16 = ops.l2norm_rows(torch.from_numpy(cand).cuda(), want_f16=True, want_f32=False)["f16"]
+    want = (c16.float() @ r16.float().T)
+    best, arg = want.max(dim=1)
+    for res in (ops.face_filter(r16, c16, 0.5, want_stats=True, band_tol=1e-3),
+                ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, flags=FLAG_NO_RECHECK,
+                                want_stats=True, band_tol=1e-3)):
+        assert res.stats["k2"]["grid_exact"] == 1, res.stats
+        got = want.gather(1, res.best_idx.long()[:, None])[:, 0]
+        # the accumulation order inside the tensor core differs from torch's: equal up to fp32 summation noise
+        assert (got - best).abs().max().item() < 2e-6
+        assert (res.best_val - best).abs().max().item() < 2e-5
+        clear = (best - torch.topk(want, 2, dim=1).values[:, 1]) > 2e-6
+        assert torch.equal(res.best_idx.long()[clear], arg[clear])
+        # the tolerance band is listed on this path too (by K2's tail, from the fp16-operand score)
+        listed = set(res.band_rows.cpu().numpy().tolist())
+        must = set(torch.nonzero((best - 0.5).abs() <= 1e-3 - 3e-5)[:, 0].cpu().numpy().tolist())
+        may = set(torch.nonzero((best - 0.5).abs() <= 1e-3 + 3e-5)[:, 0].cpu().numpy().tolist())
+        assert must <= listed <= may and len(must) > 0
+
+
+def test_two_devices_in_one_process(ops):
+    """The > 48 KB shared-memory opt-in is a per-device function attribute: the first filter on a SECOND GPU of the same
+    process must launch too (K2 and K3)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ref, cand = oracle.make_synthetic(700, 3000, 128, seed=5, n_adversarial=100, n_dup_refs=8)
+    ko, io, _ = oracle.filter_cosine(ref, cand, 0.5)
+    for d in (1, 0, 1):
+        dev = torch.device("cuda", d)
+        res = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev), 0.5, want_stats=True)
+        torch.cuda.synchronize(dev)
+        assert res.stats["path"] == "tcgen05"
+        assert np.mean(res.best_idx.cpu().numpy() == io) > 0.999

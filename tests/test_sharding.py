@@ -120,3 +120,21 @@ def test_allgather_pack_unpack_single_rank(ffr_lib, cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(k2, keep) and torch.equal(i2, idx)
     rg.close()
+
+
+@pytest.mark.gpu
+def test_allgather_inplace_single_rank(ffr_lib, cuda_dev):
+    """K4, in-place form: the filter's outputs ARE this rank's slice of the gathered arrays; one grouped NCCL launch, no
+    pack / unpack kernels of our own (launch counter unchanged by the gather)."""
+    from face_detection_and_recognition_b200 import ops
+    rg = ops.ResultGather(0, 1, 0)
+    keep_all, idx_all, keep_mine, idx_mine = rg.buffers(1237)
+    ref, cand = oracle.make_synthetic(300, 1237, 128, seed=2)
+    res = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, out=(keep_mine, idx_mine, torch.empty(1237, device="cuda")))
+    l0 = ops.launch_count()
+    k2, i2 = rg.all_gather_inplace(keep_all, idx_all)
+    torch.cuda.synchronize()
+    assert ops.launch_count() == l0
+    ko, io, _ = oracle.filter_cosine(ref, cand, 0.5)
+    assert np.mean(i2.cpu().numpy() == io) > 0.999 and k2.data_ptr() == res.keep.data_ptr()
+    rg.close()

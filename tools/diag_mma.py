@@ -10,6 +10,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from face_detection_and_recognition_b200 import _lib, ops  # noqa: E402
 
 
+def setenv(k, v):
+    os.environ[k] = str(v)
+    _lib.load().ffr_debug_reload_env()          # the library reads its FFR_* knobs once per process
+
+
+def delenv(k):
+    os.environ.pop(k, None)
+    _lib.load().ffr_debug_reload_env()
+
+
 def raw(n_ref, n_cand, dim):
     lib = _lib.load()
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -84,8 +94,9 @@ def prof(n_ref, n_cand, dim, easy=False, bench_data=False, flags=None):
         cand = torch.nn.functional.normalize(ref[0][None, :] + 0.05 * cand)
     if bench_data:                       # exactly bench.py's synthetic embeddings (half planted matches)
         import bench
-        ref = bench.make_refs(n_ref, dim, torch.device("cuda"))
-        cand = bench.make_cands(ref, 0, n_cand, torch.device("cuda"))
+        w = dict(n_ref=n_ref, dim=dim, adv_every=1250, n_dup=min(1000, n_ref // 10))
+        ref = bench.make_refs(w, torch.device("cuda"))
+        cand = bench.make_cands(w, ref, 0, n_cand, torch.device("cuda"))
     flags = ops.FLAG_NO_RECHECK if flags is None else flags
     ops.face_filter(ref, cand, 0.5, flags=flags)
     buf = torch.zeros(160 * 32, dtype=torch.int64, device="cuda")
@@ -134,9 +145,9 @@ if __name__ == "__main__":
         perf(256, 2_000_000, 128, flags=ops.FLAG_NO_RECHECK)
     if "--sweep" in sys.argv and ok:
         for b in (2, 3, 4, 5, 6):
-            os.environ["FFR_B_STAGES"] = str(b)
+            setenv("FFR_B_STAGES", str(b))
             perf(10_000, 500_000, 256, flags=ops.FLAG_NO_RECHECK, iters=3)
-        os.environ.pop("FFR_B_STAGES")
+        delenv("FFR_B_STAGES")
     if "--prof" in sys.argv:
         prof(10_000, 1_000_000, 512)
         prof(10_000, 500_000, 256)
@@ -155,11 +166,11 @@ if __name__ == "__main__":
         for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (4000, 400_000, 128), (10_000, 500_000, 256),
                       (100_000, 300_000, 128)]:
             for g in ("0", "1000000"):
-                os.environ["FFR_GRID_UPDATE_REFS"] = g
+                setenv("FFR_GRID_UPDATE_REFS", g)
                 print(f" FFR_GRID_UPDATE_REFS={g}")
                 prof(*shape)
                 perf(*shape, flags=ops.FLAG_NO_RECHECK, iters=3)
-        os.environ.pop("FFR_GRID_UPDATE_REFS")
+        delenv("FFR_GRID_UPDATE_REFS")
     if "--small" in sys.argv:
         for ex in ("auto",):
             print(f" FFR_GRID_EXACT={ex}")
@@ -183,18 +194,18 @@ if __name__ == "__main__":
         prof(1_000, 100_000, 128, bench_data=True, flags=0)
     if "--stage32" in sys.argv:
         for st in ("1",):
-            os.environ["FFR_STAGE32"] = st
+            setenv("FFR_STAGE32", st)
             print(f" FFR_STAGE32={st}")
             for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (64, 4_000_000, 128), (4000, 400_000, 128)]:
                 prof(*shape)
                 perf(*shape, iters=3)
-        os.environ.pop("FFR_STAGE32")
+        delenv("FFR_STAGE32")
     if "--st32prof" in sys.argv:
         for d in ("0", "2"):
-            os.environ["FFR_NORM_DIAG"] = d
+            setenv("FFR_NORM_DIAG", d)
             print(" FFR_NORM_DIAG", d)
             prof(256, 2_000_000, 128)
-        os.environ.pop("FFR_NORM_DIAG")
+        delenv("FFR_NORM_DIAG")
         prof(1000, 100_000, 128)
         for shape in [(1000, 100_000, 128), (256, 2_000_000, 128), (64, 4_000_000, 128), (4000, 400_000, 128)]:
             perf(*shape, iters=3)
