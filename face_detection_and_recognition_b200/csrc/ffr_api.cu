@@ -246,7 +246,8 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     if (band_count != nullptr && band_tol + delta > thr_band) thr_band = band_tol + delta;
     if (g_ev_k2_begin != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_begin, s));
     rc = launch_filter_mma(ref16, n_ref, cand16, fuse_cand, dim, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
-                           best_val, lists, recheck ? 0 : 1, band_tol, band_count, band_rows, band_cap, s);
+                           best_val, lists, recheck ? 0 : 1, band_tol, band_count, band_rows, band_cap,
+                           /*after_k1=*/dtype == FFR_DTYPE_F32, s);
     if (rc != FFR_OK) return rc;
     if (g_ev_k2_end != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_end, s));
     if (recheck) {

@@ -79,6 +79,13 @@ struct WsHeader {
 // ---- device helpers -------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// ---- programmatic dependent launch (K1 -> K2 -> K3 without launch gaps) ----
+// pdl_launch_dependents: the NEXT kernel of the stream (if it was launched with the programmatic-serialisation attribute)
+// may start now instead of when this grid has drained.  pdl_wait: blocks until the PREVIOUS grid has completed and its
+// writes are visible; a no-op for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -285,7 +292,7 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const 
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
-                      int64_t band_cap, cudaStream_t s);
+                      int64_t band_cap, bool after_k1, cudaStream_t s);
 bool filter_mma_skips_cand16(int64_t n_ref, int64_t n_cand, int32_t dim);
 void get_last_k2_config(int out[8]);
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,

@@ -493,6 +493,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     if (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // K3 is launched as a programmatic dependent: its blocks may be scheduled as soon as SMs free up and wait (pdl_wait) for
+    // this whole grid to finish -- the launch latency disappears behind our tail.  All our CTAs are already resident.
+    pdl_launch_dependents();
     if (prof_on != nullptr && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
@@ -511,6 +514,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             unsigned long long w_aempty = 0, w_bempty = 0;
             const long long t_begin = clock64();
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, a_it = 0;
+            // Programmatic dependent launch: this kernel may have started while K1 (fp16 references, and the candidates' fp16
+            // rows when K1 normalises them) is still running.  stage32 reads the ORIGINAL fp32 candidates, which K1 never
+            // touches: those loads go out first and only the first reference-tile load waits for K1.
+            bool k1_done = false;
+            if (!st32) { pdl_wait(); k1_done = true; }
             // stage32: the candidates arrive as fp32 rows in a ring of kStageRows-row staging buffers (four per tile); the
             // loads run as far ahead as the ring allows, independent of the A stages (the normaliser warps wait for those)
             const int64_t my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
@@ -555,6 +563,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 };
                 try_issue_a();
                 if (!p.decouple_a && !st32) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
+                if (!k1_done) { pdl_wait(); k1_done = true; }
                 for (int rt = 0; rt < n_rt; ++rt) {
                     const int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
                     for (int kb = 0; kb < p.kb_count; ++kb) {
@@ -960,6 +969,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // warps of ONE lane quadrant (ids 1+q / 5+q, alternating with the tile parity so that an early arrive for tile
             // n + 2 cannot complete tile n's barrier); with CTA-wide barriers every quadrant waited for the slowest warp.
             const long long t_tail0 = pr ? clock64() : 0;
+            if (first_tile) pdl_wait();                          // the re-check header the appends below count in is zeroed by K1
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
             if (!merger) {
@@ -1172,7 +1182,7 @@ struct BandArgs { float tol; int32_t* count; int64_t* rows; int64_t cap; };
 int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                            int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                           RecheckLists lists, int no_recheck, BandArgs band, float* dbg_scores, cudaStream_t s) {
+                           RecheckLists lists, int no_recheck, BandArgs band, float* dbg_scores, bool after_k1, cudaStream_t s) {
     if (dim_pad % kBlockK != 0 || dim_pad < kBlockK || dim_pad > 512) {
         set_error("filter_mma: padded dim %d not in {64..512 step 64}", dim_pad);
         return FFR_ERR_UNSUPPORTED;
@@ -1311,11 +1321,16 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     cfg.blockDim = dim3(64 + 32 * ew + (fuse ? 64 : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (after_k1 && kn.pdl != 0) {       // the previous launch of this stream is K1 (it triggers its dependents at entry)
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tm_c, tm_r, tm_c32, p));
     FFR_LAUNCH_CHECK("filter_mma");
     return FFR_OK;
@@ -1346,9 +1361,10 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const 
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
-                      int64_t band_cap, cudaStream_t s) {
+                      int64_t band_cap, bool after_k1, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, cand16, cand32, dim, n_cand, dim_pad, thr, delta, thr_band, ref_index_base,
-                                  keep, idx, val, lists, no_recheck, BandArgs{band_tol, band_count, band_rows, band_cap}, nullptr, s);
+                                  keep, idx, val, lists, no_recheck, BandArgs{band_tol, band_count, band_rows, band_cap}, nullptr,
+                                  after_k1, s);
 }
 
 // true when the fused schedule needs NO fp16 copy of the candidates in the workspace (stage32: the fp16 A tiles only ever
@@ -1370,7 +1386,7 @@ int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* ca
                             float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                             float* scores, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, const_cast<__half*>(cand16), nullptr, dim_pad, n_cand, dim_pad, thr, delta, delta, 0, keep, idx,
-                                  val, lists, 0, BandArgs{0.f, nullptr, nullptr, 0}, scores, s);
+                                  val, lists, 0, BandArgs{0.f, nullptr, nullptr, 0}, scores, false, s);
 }
 
 }  // namespace ffr

@@ -41,6 +41,7 @@ l2norm_rows_vec_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t di
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    pdl_launch_dependents();            // K2 may start its prologue / candidate staging now; it waits (pdl_wait) before it reads our output
     if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
     const int64_t rows = rows_a + sec.rows;
 
@@ -112,6 +113,7 @@ l2norm_rows_sub_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_t di
     const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    pdl_launch_dependents();            // K2 may start its prologue / candidate staging now; it waits (pdl_wait) before it reads our output
     if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
     const int64_t rows = rows_a + sec.rows;
     for (int64_t r0 = warp * (kGroups * kRowsPerWarp); r0 < rows; r0 += nwarps * (kGroups * kRowsPerWarp)) {
@@ -164,6 +166,7 @@ l2norm_rows_generic_kernel(const float* __restrict__ x_a, int64_t rows_a, int32_
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kThreads) >> 5;
+    pdl_launch_dependents();            // K2 may start its prologue / candidate staging now; it waits (pdl_wait) before it reads our output
     if (blockIdx.x == 0 && threadIdx.x < sec.zero_words) sec.zero_ptr[threadIdx.x] = 0u;
     const int64_t rows = rows_a + sec.rows;
     for (int64_t rv = warp; rv < rows; rv += nwarps) {

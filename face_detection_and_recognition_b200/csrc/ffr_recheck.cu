@@ -292,6 +292,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
     __shared__ unsigned long long s_key[kWarps][kFullGroup];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    pdl_wait();                 // launched as K2's programmatic dependent: everything below reads K2's lists and outputs
     recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
                         band_rows, band_cap, kVec);
     int64_t count = lists.hdr->full_count;
@@ -525,10 +526,20 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
             attr_set[slot] = true;
         }
     }
-    if (vec) recheck_kernel<true><<<g2, kThreads, smem_full, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                                              lists, band_tol, band_count, band_rows, band_cap);
-    else     recheck_kernel<false><<<g2, kThreads, smem, s>>>(ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                                               lists, band_tol, band_count, band_rows, band_cap);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = g2;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = vec ? smem_full : smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // K2 (the previous launch) triggers at its entry
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = knobs().pdl != 0 ? 1 : 0;
+    if (vec) FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<true>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                             lists, band_tol, band_count, band_rows, band_cap));
+    else     FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<false>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
+                                             lists, band_tol, band_count, band_rows, band_cap));
     FFR_LAUNCH_CHECK("recheck");
     return FFR_OK;
 }

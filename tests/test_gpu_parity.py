@@ -429,7 +429,7 @@ def _large_gallery(n_ref, n_cand, dim, seed):
     near-duplicate pairs (so the near ties are actually leading)."""
     ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=seed, n_adversarial=1000, n_dup_refs=1000)
     rng = np.random.default_rng(seed + 1)
-    offs = (3, 9, 40, 130, 300, 70_000)
+    offs = (3, 9, 40, 130, 300, (n_ref * 7) // 10)
     src = rng.integers(0, n_ref // 4, 600)
     for k, i in enumerate(src):
         j = int(i) + offs[k % len(offs)]
