@@ -68,11 +68,9 @@ int env_int(const char* name, int dflt) {
 const Knobs* read_knobs() {
     Knobs* k = new Knobs();
     k->cta_group = env_int("FFR_CTA_GROUP", 2);
-    k->a_tmem = env_int("FFR_A_TMEM", 0);
     k->a_stages = env_int("FFR_A_STAGES", 0);
     k->b_stages = env_int("FFR_B_STAGES", 0);
     k->acc_stages = env_int("FFR_ACC_STAGES", 2);
-    k->epi_warps = env_int("FFR_EPI_WARPS", 8);
     k->diag_half_b = env_int("FFR_DIAG_HALF_B", 0);
     k->epi_mode = env_int("FFR_EPI_MODE", 0);
     k->discard_a = env_int("FFR_DISCARD_A", 1);
@@ -336,7 +334,7 @@ int ffr_filter(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand,
                          best_idx, best_val, 0.f, nullptr, nullptr, 0, 0, workspace, ws_bytes, stream);
 }
 
-int ffr_filter_stats(const void* workspace, int64_t out[4], ffr_stream_t stream) {
+int ffr_filter_stats(const void* workspace, int64_t out[8], ffr_stream_t stream) {
     if (workspace == nullptr || out == nullptr) { set_error("filter_stats: null argument"); return FFR_ERR_INVALID; }
     WsHeader h;
     FFR_CUDA_TRY(cudaMemcpyAsync(&h, workspace, sizeof(h), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
@@ -344,6 +342,8 @@ int ffr_filter_stats(const void* workspace, int64_t out[4], ffr_stream_t stream)
     out[0] = h.recheck_count; out[1] = h.full_count;
     out[2] = g_last.ws == workspace ? g_last.path : -1;
     out[3] = g_last.ws == workspace ? g_last.launches : -1;
+    out[4] = h.part_count;
+    out[5] = out[6] = out[7] = 0;
     return FFR_OK;
 }
 

@@ -37,7 +37,7 @@ constexpr int kMaxDevices = 64;
 // Read from the environment ONCE per process (first use); the hot path never calls getenv.  Tests that flip a knob
 // between calls use the non-ABI hook ffr_debug_reload_env().  -1 = "auto" where a knob has a shape-dependent default.
 struct Knobs {
-    int cta_group, a_tmem, a_stages, b_stages, acc_stages, epi_warps, diag_half_b, epi_mode, discard_a, decouple_a,
+    int cta_group, a_stages, b_stages, acc_stages, diag_half_b, epi_mode, discard_a, decouple_a,
         norm_evict_first, norm_diag, grid_update_refs, grid_exact, norm_ahead, fuse_k1, stage32, k1_blocks_per_sm,
         k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, small_n, pdl;
 };
@@ -59,7 +59,8 @@ constexpr int kFullGroup = 8;
 struct WsHeader;
 struct RecheckLists {
     WsHeader* hdr;
-    RecheckRec* recs;          // near-tie / near-threshold rows: two-candidate fp32 check (K3a)
+    RecheckRec* recs;          // near-tie / near-threshold rows: two-candidate fp32 check (K3a) from the front; part-rescan
+                               // records {row, first reference of the part, two more candidates} from the back
     int64_t rec_cap;
     int32_t* full_rows;        // rows needing the full rescan (K3b)
     unsigned long long* full_keys;   // per full row: (orderable(best) << 32) | ~idx, combined with atomicMax
@@ -73,7 +74,8 @@ struct WsHeader {
     int32_t full_count;      // of which need the full rescan
     int32_t path;            // 0 fp32, 1 mma
     int32_t launches;
-    int32_t pad[60];
+    int32_t part_count;      // rows whose hidden columns all lie in one 128-reference part (records at the END of recs, growing down)
+    int32_t pad[59];
 };
 
 // ---- device helpers -------------------------------------------------------------------------------

@@ -57,13 +57,23 @@ constexpr uint32_t kBarrierBytes = 1024;                      // mbarriers + TME
 constexpr int kStageRows = 32;                                // stage32: fp32 candidate rows per staging buffer
 constexpr uint32_t kStageBytes = kStageRows * 128 * 4;        // 16 KiB: 32 rows x 128 floats (dim_pad == 128 only)
 constexpr int kMaxSBufs = 6;
-constexpr uint32_t kMergeBytes = kTileM * 8 * 4;              // top-4 + amb hand-over of the upper column half
+constexpr uint32_t kMergeBytes = kTileM * 10 * 4;             // top-4 + hidden-column state hand-over of the other column half
 // per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
 // running top-4 scores of one candidate (first three with their reference index): what K3 needs to decide in fp32
 struct Top3 {
     float b1, b2, b3, b4;
     int32_t i1, i2, i3;
+};
+
+// Columns that were inside the window when they were seen but were NOT inserted one by one.  amb = the largest maximum of a
+// 128-column part with several in-window columns (flag-only update path) and base = that part's first reference; amb2 = the
+// largest such maximum of any OTHER part or 32-column chunk (exact path: further in-window columns of a chunk).  At the end
+// of the candidate tile: amb2 still inside the window -> the whole reference set is rescanned in fp32 (K3b); only amb inside
+// it -> K3 rescans just the 128 references of that part; neither -> nothing hidden matters any more.
+struct Hidden {
+    float amb, amb2;
+    int32_t base;
 };
 
 __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
@@ -102,7 +112,7 @@ __device__ __forceinline__ void top3_merge_insert(Top3& t, float v, int32_t idx)
 // irrelevant.  This keeps the path to ~110 instructions; the ordered insertion of every in-window column it
 // replaces was ~600 and made the whole loop body too large for the instruction cache to stream.
 __device__ __forceinline__ void update_chunk(const float (&v)[32], float cmax, int32_t base, float delta, Top3& t,
-                                             float& gate, float& amb) {
+                                             float& gate, float& amb) {           // amb: Hidden::amb2 of the caller
     const float w = fmaxf(t.b1, cmax) - delta;
     uint32_t g[4];
 #pragma unroll
@@ -218,7 +228,7 @@ struct MaxTree<1> {
 // than w0: the window only gets wider, and the fall-back path uses w0 itself.)
 template <int kC>
 __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const float (&sx)[kC][4], const float (&cm)[kC], float m,
-                                            int32_t base0, float delta, bool exact, Top3& t, float& gate, float& amb) {
+                                            int32_t base0, float delta, bool exact, Top3& t, float& gate, Hidden& hid) {
     constexpr float kBig = 1152921504606846976.0f;     // 2^60
     const float w0 = fmaxf(t.b1, m) - delta;
     const float w1 = fmaf(fabsf(w0), -1.1920929e-7f, w0) - 1.0e-30f;
@@ -245,18 +255,22 @@ __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const floa
     if (exact && multi) {
         // (a fall-back at 8-column granularity -- one divergent region per X group at the floor -- gave fewer full rescans
         // but was slower than the per-chunk masks: 16 reconvergence regions in the loop body cost more than they save)
-        update_part<kC>(v, cm, m, base0, delta, t, gate, amb);
+        update_part<kC>(v, cm, m, base0, delta, t, gate, hid.amb2);
         return;
     }
     // !exact: no second path at all.  "Rare per thread" is not rare per accumulator stage -- the MMA waits for the slowest
     // of the 16 warps of a CTA pair, and with ~0.3 % of (row, part) pairs taking a 400-instruction detour most tiles had one.
-    // Instead the part maximum goes in with a placeholder column and the row remembers it in `amb` (as update_chunk does
-    // for several columns of one chunk): if it is still within delta of the final best the row gets the full fp32 rescan,
-    // which recomputes index, score and keep from every reference; if not, nothing of this part matters any more.
+    // Instead the part maximum goes in with a placeholder column (the part's first) and the row remembers the part: if its
+    // maximum is still within delta of the final best, K3 rescans the 128 references of THAT part in fp32 (plus the row's
+    // other tracked candidates) -- or every reference, if a second such part is inside the window too; if it is not, nothing
+    // of this part matters any more.
     // (sums < 1: the part is below the window, or NaN scores of a zero-norm row -- inserting -inf is a no-op)
     const float ins = fminf(sxa, sya) >= 1.0f ? m : -INFINITY;
     const int32_t col = multi ? 0 : __float2int_rn(fmaf(sxa - 1.0f, 512.0f, (sya - 1.0f) * 64.0f));     // 8 a + b
-    amb = multi ? fmaxf(amb, m) : amb;
+    const bool lead = multi && m > hid.amb;
+    hid.amb2 = multi ? fmaxf(hid.amb2, fminf(hid.amb, m)) : hid.amb2;
+    hid.amb = lead ? m : hid.amb;
+    hid.base = lead ? base0 : hid.base;
     top3_insert(t, ins, base0 + col);
     gate = t.b1 - delta;
 }
@@ -324,30 +338,6 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {         // arri
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
         ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
 }
-// ---- A operand in tensor memory ("TS" form): D[tmem] (+)= A[tmem] * B[smem desc]^T ----------------------------
-// A tile layout in TMEM: lane = candidate row, one 32-bit column holds two consecutive K elements, so a K = 16 MMA step
-// reads 8 columns.  tcgen05.cp .128x256b copies exactly such a slice (128 rows x 32 bytes) out of the K-major
-// SWIZZLE_128B staging tile, described by the same matrix descriptor the SS-form MMA would have used for A.
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc, bool cg2) {
-    if (cg2) asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-    else     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-}
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate, bool cg2) {
-    if (cg2)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -420,14 +410,17 @@ struct KParams {
     unsigned long long* prof;      // optional [gridDim.x][32] stall-cycle counters (diagnostics)
 };
 
-// kCG: tcgen05 cta_group (1|2).  kEW: epilogue warps (8) = 4 TMEM lane quadrants x kEW/4 column parts.
+// kCG: tcgen05 cta_group (1|2).  Eight epilogue warps = 4 TMEM lane quadrants x 2 column halves.
 // kNormMode != 0 (kNorm): K1 for the candidates runs INSIDE this kernel.  Two extra "normaliser" warps (the hardware allocates warps in
 // fours, so 10 warps cost 12 anyway) read the fp32 rows of the CTA's NEXT candidate tile, L2-normalise them exactly like K1
 // and write the fp16 rows into the workspace, while the tensor core works on the current tile; the TMA producer waits
 // for a per-CTA counter before it loads a tile.  The rows come back through L2, HBM sees the fp32 embeddings once, and
 // the 0.6 ms K1 pass over 1.25 M x 512 disappears behind the MMAs (the kernel needs < 10 % of K1's bandwidth).
-template <int kCG, int kEW, int kNormMode, int kAccN, bool kInstr>
-__global__ void __launch_bounds__(64 + 32 * kEW + (kNormMode ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
+// kExact / kAlways: the two epilogue policies as COMPILE-TIME constants (0 | 1; 2 = read the run-time flag, used by the
+// instrumented build and cta_group::1).  kExact = 0 removes the ~1100-instruction exact fall-back (update_part) from the
+// hot loop's body altogether; kAlways picks the unconditional or the gated update path.
+template <int kCG, int kNormMode, int kExact, int kAlways, bool kInstr>
+__global__ void __launch_bounds__(64 + 32 * 8 + (kNormMode ? 64 : 0), 1)   // 10 warps are allocated as 12: <= 168 registers
 filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_constant__ CUtensorMap tmap_ref,
                   const __grid_constant__ CUtensorMap tmap_cand32, const KParams p) {
     // kNormMode: 0 = the candidates' fp16 rows come from K1, 1 = normaliser warps with global loads + fp16 scratch, 2 = stage32.
@@ -436,12 +429,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     // instantiation contains none of it: the counters alone were half a dozen spilled 64-bit values per role.
     constexpr bool kNorm = kNormMode != 0;
     constexpr bool st32 = kNormMode == 2;
+    constexpr int kEW = 8;                                          // epilogue warps
+    constexpr int kAccN = kTileN;                                   // references per accumulator stage
     const unsigned long long* const prof_on = kInstr ? p.prof : nullptr;
     constexpr int kParts = kEW / 4;                                 // column parts per reference tile
-    constexpr bool kTS = kAccN != kTileN;                           // A operand in tensor memory (kAccN 192 | 128), else shared memory
     constexpr int kChunksPerPart = (kAccN / 32) / kParts;
     constexpr uint32_t kBRows = kAccN / kCG;                        // B rows this CTA loads per K-block
-    constexpr uint32_t kATmemCol = 2 * kAccN;                       // kTS: first TMEM column of the A tile (after both accumulator stages)
     constexpr uint32_t kBStageBytes = kBRows * kBlockK * 2;         // 32 KiB (kCG 1) / 16 KiB (kCG 2)
     extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t a_stage_bytes = static_cast<uint32_t>(p.kb_count) * kABlockBytes;
@@ -621,24 +614,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(smem_a + as * a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-                if constexpr (kTS) {
-                    // staging tile -> tensor memory, one 128 x 32-byte slice per K = 16 step.  tcgen05.cp and tcgen05.mma
-                    // execute in issue order, so these copies queue behind the previous tile's MMAs (which still read the
-                    // old A columns) and ahead of this tile's; the commit hands the staging tile back to the TMA producer
-                    // as soon as the copies have read it -- the next tile's A loads overlap this tile's MMAs.
-                    for (int kb = 0; kb < p.kb_count; ++kb) {
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k)
-                            tmem_cp_128x256b(tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u,
-                                             kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k), kCG == 2);
-                    }
-                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);
-                }
                 for (int rt = 0; rt < n_rt; ++rt) {
                     mbar_wait_timed(&t_empty[acc], tph ^ 1, pr, w_tempty);
                     tc_fence_after();
                     uint32_t idesc = idesc_full;
-                    if (kCG == 1 && !kTS) {                     // tail reference tile: only as many columns as needed
+                    if (kCG == 1) {                             // tail reference tile: only as many columns as needed
                         // (the cta_group::2 analogue -- N = 2 * ceil16(live) when the live references sit in CTA 0's half --
                         // is correct but did not pay: an N = 32 MMA costs ~100 cycles, and the same-box wall clock got worse)
                         const int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kAccN;
@@ -653,13 +633,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         for (int k = 0; k < kSteps; ++k) {
                             const uint64_t db = kDescHi64 | (b_lo + 2u * k);
                             const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-                            if constexpr (kTS) {
-                                umma_f16_ts(d_tmem, tmem_base + kATmemCol + static_cast<uint32_t>(kb * kSteps + k) * 8u, db, idesc, accum, kCG == 2);
-                            } else {
-                                const uint64_t da = kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k);
-                                if (kCG == 2) umma_f16_cg2(d_tmem, da, db, idesc, accum);
-                                else          umma_f16(d_tmem, da, db, idesc, accum);
-                            }
+                            const uint64_t da = kDescHi64 | (a_lo0 + kb * (kABlockBytes >> 4) + 2u * k);
+                            if (kCG == 2) umma_f16_cg2(d_tmem, da, db, idesc, accum);
+                            else          umma_f16(d_tmem, da, db, idesc, accum);
                         }
                         if (kCG == 2) umma_commit_cg2(&b_empty[bs]); else umma_commit(&b_empty[bs]);   // B stage reusable
                         if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1; }
@@ -668,9 +644,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (p.acc_stages == 2) { acc ^= 1u; if (acc == 0u) tph ^= 1u; } else { tph ^= 1u; }
                     ++t_it;
                 }
-                if constexpr (!kTS) {
-                    if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);       // A stage reusable
-                }
+                if (kCG == 2) umma_commit_cg2(&a_empty[as]); else umma_commit(&a_empty[as]);           // A stage reusable
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
             if (pr) {
@@ -873,8 +847,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         unsigned long long w_tfull = 0, c_hot = 0, c_gen = 0, c_bar1 = 0, c_tail = 0;
         // diagnostics (score dump, epilogue modes) only exist in the general loop
         const bool hot_ok = !kInstr || (p.dbg_scores == nullptr && p.epi_mode == 0);
-        const bool grid_updates = p.grid_updates != 0;           // ... and update_grid
-        const bool grid_exact = p.grid_exact != 0;               // several in-window columns in one part: exact masks, or flag the row
+        // the two epilogue policies: compile-time constants in the production instantiations
+        const bool grid_updates = kAlways == 2 ? p.grid_updates != 0 : kAlways == 1;     // unconditional update path
+        const bool grid_exact = kExact == 2 ? p.grid_exact != 0 : kExact == 1;           // several in-window columns in one part: exact masks, or flag the row
         const long long t_begin = clock64();
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
             Top3 t;
@@ -882,7 +857,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             t.i1 = 0;
             t.i2 = t.i3 = -1;
             float gate = -INFINITY;                             // running best - delta
-            float amb = -INFINITY;                              // see update_chunk
+            Hidden hid;                                         // see struct Hidden
+            hid.amb = hid.amb2 = -INFINITY;
+            hid.base = 0;
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             for (int rt = 0; rt < n_rt; ++rt) {
                 const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
@@ -930,7 +907,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     // short reference sets: some lane of the warp sets a record on nearly every tile, so the update runs
                     // unconditionally and branch-free; long ones: behind one branch on the part maximum.  (Round-1c's
                     // per-chunk update paths are gone from this loop: dead code in it costs wall clock.)
-                    if (grid_updates || m >= gate) update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, amb);
+                    if (grid_updates || m >= gate) update_grid<kChunksPerPart>(v, sx, cm, m, base0, p.delta, grid_exact, t, gate, hid);
                     if (pr) c_hot += static_cast<unsigned long long>(clock64() - tp0);
                 } else {
                     // ---- general loop, one chunk at a time: diagnostics only (score dump, epilogue modes)
@@ -950,7 +927,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (p.epi_mode == 1) { t.b1 = fmax3(t.b1, va[0], va[31]); continue; }
                         const float cmx = chunk_max(va);
                         if (p.epi_mode == 2) { t.b1 = fmaxf(t.b1, cmx); continue; }
-                        if (cmx >= gate) update_chunk(va, cmx, base0 + cc * 32, p.delta, t, gate, amb);
+                        if (cmx >= gate) update_chunk(va, cmx, base0 + cc * 32, p.delta, t, gate, hid.amb2);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -973,7 +950,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
             if (!merger) {
-                float* mg = merge + (kAlt ? 0 : (h - 1) * 8 * kTileM);
+                float* mg = merge + (kAlt ? 0 : (h - 1) * 10 * kTileM);
                 if (!kAlt && !first_tile) named_bar_sync(5 + q, kParts * 32);  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
@@ -982,7 +959,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mg[4 * kTileM + r_in_tile] = __int_as_float(t.i1);
                 mg[5 * kTileM + r_in_tile] = __int_as_float(t.i2);
                 mg[6 * kTileM + r_in_tile] = __int_as_float(t.i3);
-                mg[7 * kTileM + r_in_tile] = amb;
+                mg[7 * kTileM + r_in_tile] = hid.amb;
+                mg[8 * kTileM + r_in_tile] = hid.amb2;
+                mg[9 * kTileM + r_in_tile] = __int_as_float(hid.base);
                 __threadfence_block();
                 named_bar_arrive(bar_ready, kParts * 32);
             } else {
@@ -993,12 +972,17 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 int32_t oi[kParts - 1][3];
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    const float* mg = merge + pp * 8 * kTileM;
+                    const float* mg = merge + pp * 10 * kTileM;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
 #pragma unroll
                     for (int e = 0; e < 3; ++e) oi[pp][e] = __float_as_int(mg[(4 + e) * kTileM + r_in_tile]);
-                    amb = fmaxf(amb, mg[7 * kTileM + r_in_tile]);
+                    // the other half's hidden-column state: the larger part maximum leads, everything else is "a second part"
+                    const float o_amb = mg[7 * kTileM + r_in_tile], o_amb2 = mg[8 * kTileM + r_in_tile];
+                    const int32_t o_base = __float_as_int(mg[9 * kTileM + r_in_tile]);
+                    hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
+                    hid.base = o_amb > hid.amb ? o_base : hid.base;
+                    hid.amb = fmaxf(hid.amb, o_amb);
                 }
                 if (!kAlt) named_bar_arrive(5 + q, kParts * 32);
 #pragma unroll
@@ -1012,9 +996,13 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 const bool valid = row < p.n_cand;
                 const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
                 const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
-                const bool hidden = amb > -INFINITY && amb >= t.b1 - p.delta;                 // un-inserted columns may be inside the window
+                // un-inserted columns may be inside the window: of ONE part (K3 rescans its 128 references), or of more
+                const bool hid2 = hid.amb2 > -INFINITY && hid.amb2 >= t.b1 - p.delta;
+                const bool hid1 = hid.amb > -INFINITY && hid.amb >= t.b1 - p.delta;
+                const bool hidden = hid1 || hid2;
                 const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hidden);
-                const bool full = flagged && (hidden || t.b1 - t.b4 <= p.delta);   // four or more inside the window: full rescan
+                const bool full = flagged && (hid2 || t.b1 - t.b4 <= p.delta);     // four or more inside the window, or hidden ones anywhere: full rescan
+                const bool part = flagged && !full && hid1;                        // hidden columns in one known part
                 if (valid) {
                     p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
                     p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
@@ -1024,9 +1012,34 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (p.band_rows != nullptr && slot < p.band_cap) p.band_rows[slot] = row;
                     }
                 }
-                const bool pair = flagged && !full;
+                const bool pair = flagged && !full && !part;
                 const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
                 const uint32_t umask = __ballot_sync(0xffffffffu, full);
+                const uint32_t qmask = __ballot_sync(0xffffffffu, part);
+                if (qmask != 0) {                                  // part-rescan records grow DOWN from the end of the record array
+                    int32_t slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->part_count, __popc(qmask));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (part) {
+                        // a row is in exactly one list, so the two ends of the array never meet.  The part's own placeholder entry
+                        // (and anything else inside the part) is covered by the part scan; at most two tracked candidates lie outside
+                        const int64_t slot = p.lists.rec_cap - 1 - (slot0 + __popc(qmask & ((1u << lane) - 1)));
+                        const auto outside = [&](float b, int32_t i) {
+                            return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / kParts);
+                        };
+                        int32_t e[2] = {-1, -1};
+                        int ne = 0;
+                        if (outside(t.b1, t.i1)) e[ne++] = t.i1;
+                        if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
+                        if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
+                        RecheckRec r;
+                        r.row = static_cast<int32_t>(row);
+                        r.idx1 = hid.base;
+                        r.idx2 = e[0];
+                        r.idx3 = e[1];
+                        if (slot >= 0) p.lists.recs[slot] = r;
+                    }
+                }
                 if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
                     int32_t slot0 = 0;
                     if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->recheck_count, __popc(pmask));
@@ -1199,26 +1212,17 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (cg != 2 || (sms & 1)) cg = 1;
     const bool fuse = cand32 != nullptr;
     const int kb = dim_pad / kBlockK;
-    // A operand in tensor memory (cta_group::2 only, FFR_A_TMEM=1): the A tile leaves shared memory for 32 TMEM columns per
-    // K-block (tcgen05.cp from a single staging tile), the accumulator stages shrink to 192 (dim <= 256) or 128 columns and
-    // the B ring gets the rest of shared memory.  Correct (same tests), but measured SLOWER than the SS form on B200: an
-    // N = 128 / 192 MMA with A in TMEM costs ~108 / ~144 cycles against 64 / 96 ideal, while the SS form's N = 256 MMA runs
-    // at ~141 of 128 -- per 256 reference columns 6898 vs 4526 cycles at dim 512, 1539 vs 1374 at dim 128.  Off by default.
-    int acc_n = kTileN;
-    if (cg == 2 && kn.a_tmem != 0) acc_n = dim_pad <= 256 ? 192 : 128;
-    const bool ts = acc_n != kTileN;
+    constexpr int acc_n = kTileN;
     const uint32_t a_stage = kb * kABlockBytes;
     const uint32_t b_stage = (acc_n / cg) * kBlockK * 2;
-    int a_stages = ts ? 1 : (kn.a_stages > 0 ? kn.a_stages : a_stage_count(dim_pad));
+    int a_stages = kn.a_stages > 0 ? kn.a_stages : a_stage_count(dim_pad);
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
-    // epilogue warps: 8 = 4 TMEM lane quadrants x 2 column parts.  FFR_EPI_WARPS=16 (SS form, cta_group::2 only) splits the
-    // columns four ways: twice the warps per scheduler to hide the TMEM-load and max-tree latencies, at <= 102 registers.
-    const int ew = (cg == 2 && kn.epi_warps == 16 && kn.a_tmem == 0) ? 16 : 8;
+    constexpr int ew = 8;                                  // epilogue warps: 4 TMEM lane quadrants x 2 column halves
     const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
     // MMAs read the other), the B ring gets what is left (>= 2 stages)
-    const bool st32 = fuse && !ts && ew == 8 && filter_mma_stage32_ok(dim, dim_pad);
+    const bool st32 = fuse && filter_mma_stage32_ok(dim, dim_pad);
     int s_bufs = st32 ? kMaxSBufs : 0;
     if (st32) {
         a_stages = 2;
@@ -1266,33 +1270,31 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.norm_evict_first = kn.norm_evict_first;
     p.norm_diag = kn.norm_diag;
     p.grid_updates = n_ref <= kn.grid_update_refs ? 1 : 0;
-    // The flag-only form turns every same-part near tie into a full fp32 rescan (~ near-tie fraction / parts of the rows):
-    // measured a win only where the epilogue paces the kernel AND there are hundreds of parts (100 k x 128-d: 6.14 -> 5.81 ms
-    // with K3; 1 k / 4 k / 10 k references: K3 loses more than K2 gains).  It RELIES on K3: without the re-check (fp16 input,
-    // FFR_FLAG_NO_RECHECK, the score dump) the placeholder index it inserts would be the final answer, so those callers
-    // always get the exact per-column masks.
-    p.grid_exact = kn.grid_exact >= 0 ? kn.grid_exact : ((dim_pad <= 128 && n_ref >= 32768) ? 0 : 1);
+    // The flag-only form hands every same-part near tie to K3, which rescans the 128 references of that part in fp32 (round
+    // 1 rescanned ALL references, which only paid for 128-d x >= 32 k references).  It RELIES on K3: without the re-check
+    // (fp16 input, FFR_FLAG_NO_RECHECK, the score dump) the placeholder index it inserts would be the final answer, so those
+    // callers always get the exact per-column masks (FFR_GRID_EXACT=1 forces them everywhere).
+    p.grid_exact = kn.grid_exact >= 0 ? kn.grid_exact : 0;
     if (no_recheck || dbg_scores != nullptr) p.grid_exact = 1;
     p.norm_ahead = kn.norm_ahead < 1 ? 1 : kn.norm_ahead;
 
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
-    // the instrumented instantiations exist for the default tile shape only (what tools/diag_mma.py and the tests' score dump use)
-    const bool instr = (prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0) && ew == 8 && acc_n == 256;
+    // Instantiations: cta_group::2 production kernels carry the two epilogue policies as compile-time constants (no dead
+    // fall-back code in the hot loop); the instrumented build (tools/diag_mma.py, the tests' score dump) and the
+    // cta_group::1 fall-back (odd SM counts, FFR_CTA_GROUP=1) read them at run time.
+    const bool instr = prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0;
+    const int nm = st32 ? 2 : (fuse ? 1 : 0);
+#define FFR_K(CG, NM, E, A, I) filter_mma_kernel<CG, NM, E, A, I>
+#define FFR_K_POLICY(NM) {FFR_K(2, NM, 0, 0, false), FFR_K(2, NM, 0, 1, false), FFR_K(2, NM, 1, 0, false), FFR_K(2, NM, 1, 1, false)}
+    static const KernelFn prod2[3][4] = {FFR_K_POLICY(0), FFR_K_POLICY(1), FFR_K_POLICY(2)};
+    static const KernelFn instr2[3] = {FFR_K(2, 0, 2, 2, true), FFR_K(2, 1, 2, 2, true), FFR_K(2, 2, 2, 2, true)};
+    static const KernelFn prod1[3] = {FFR_K(1, 0, 2, 2, false), FFR_K(1, 1, 2, 2, false), FFR_K(1, 2, 2, 2, false)};
+    static const KernelFn instr1[3] = {FFR_K(1, 0, 2, 2, true), FFR_K(1, 1, 2, 2, true), FFR_K(1, 2, 2, 2, true)};
+#undef FFR_K_POLICY
+#undef FFR_K
     KernelFn fn;
-    if (ew == 16)          fn = fuse ? filter_mma_kernel<2, 16, 1, 256, false> : filter_mma_kernel<2, 16, 0, 256, false>;
-    else if (acc_n == 192) fn = fuse ? filter_mma_kernel<2, 8, 1, 192, false> : filter_mma_kernel<2, 8, 0, 192, false>;
-    else if (acc_n == 128) fn = fuse ? filter_mma_kernel<2, 8, 1, 128, false> : filter_mma_kernel<2, 8, 0, 128, false>;
-    else if (cg == 1) {
-        if (instr) fn = st32 ? filter_mma_kernel<1, 8, 2, 256, true> : fuse ? filter_mma_kernel<1, 8, 1, 256, true> : filter_mma_kernel<1, 8, 0, 256, true>;
-        else       fn = st32 ? filter_mma_kernel<1, 8, 2, 256, false> : fuse ? filter_mma_kernel<1, 8, 1, 256, false> : filter_mma_kernel<1, 8, 0, 256, false>;
-    } else {
-        if (instr) fn = st32 ? filter_mma_kernel<2, 8, 2, 256, true> : fuse ? filter_mma_kernel<2, 8, 1, 256, true> : filter_mma_kernel<2, 8, 0, 256, true>;
-        else       fn = st32 ? filter_mma_kernel<2, 8, 2, 256, false> : fuse ? filter_mma_kernel<2, 8, 1, 256, false> : filter_mma_kernel<2, 8, 0, 256, false>;
-    }
-    if ((dbg_scores != nullptr || p.epi_mode != 0) && !instr) {
-        set_error("filter_mma: score dump / epilogue diagnostics need the default tile shape (FFR_EPI_WARPS=8, FFR_A_TMEM=0)");
-        return FFR_ERR_UNSUPPORTED;
-    }
+    if (cg == 2) fn = instr ? instr2[nm] : prod2[nm][(p.grid_exact ? 2 : 0) + (p.grid_updates ? 1 : 0)];
+    else         fn = instr ? instr1[nm] : prod1[nm];
     // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: set once per device this process uses
     {
         static std::mutex mu;
@@ -1300,14 +1302,13 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
         const int slot = current_device_slot();
         std::lock_guard<std::mutex> lock(mu);
         if (!attr_set[slot]) {
-            KernelFn all[] = {filter_mma_kernel<1, 8, 0, 256, false>, filter_mma_kernel<1, 8, 1, 256, false>, filter_mma_kernel<1, 8, 2, 256, false>,
-                              filter_mma_kernel<2, 8, 0, 256, false>, filter_mma_kernel<2, 8, 1, 256, false>, filter_mma_kernel<2, 8, 2, 256, false>,
-                              filter_mma_kernel<1, 8, 0, 256, true>, filter_mma_kernel<1, 8, 1, 256, true>, filter_mma_kernel<1, 8, 2, 256, true>,
-                              filter_mma_kernel<2, 8, 0, 256, true>, filter_mma_kernel<2, 8, 1, 256, true>, filter_mma_kernel<2, 8, 2, 256, true>,
-                              filter_mma_kernel<2, 8, 1, 192, false>, filter_mma_kernel<2, 8, 0, 192, false>,
-                              filter_mma_kernel<2, 8, 1, 128, false>, filter_mma_kernel<2, 8, 0, 128, false>,
-                              filter_mma_kernel<2, 16, 1, 256, false>, filter_mma_kernel<2, 16, 0, 256, false>};
-            for (KernelFn f : all) FFR_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            for (int m = 0; m < 3; ++m) {
+                for (int v = 0; v < 4; ++v)
+                    FFR_CUDA_TRY(cudaFuncSetAttribute(prod2[m][v], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                FFR_CUDA_TRY(cudaFuncSetAttribute(instr2[m], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                FFR_CUDA_TRY(cudaFuncSetAttribute(prod1[m], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                FFR_CUDA_TRY(cudaFuncSetAttribute(instr1[m], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            }
             attr_set[slot] = true;
         }
     }
@@ -1373,7 +1374,7 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const 
 bool filter_mma_skips_cand16(int64_t n_ref, int64_t n_cand, int32_t dim) {
     const int32_t dim_pad = (dim + 63) / 64 * 64;
     const Knobs& kn = knobs();
-    if (kn.cta_group != 2 || (num_sms() & 1) || kn.a_tmem != 0 || kn.epi_warps == 16) return false;
+    if (kn.cta_group != 2 || (num_sms() & 1)) return false;
     if (!filter_mma_stage32_ok(dim, dim_pad)) return false;
     return filter_mma_can_fuse(reinterpret_cast<const float*>(uintptr_t(256)), n_ref, n_cand, dim, dim_pad);
 }

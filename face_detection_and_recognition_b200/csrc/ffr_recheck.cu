@@ -193,6 +193,97 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
     idx = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFull));
 }
 
+// K3p: rows whose un-inserted in-window columns all lie in ONE 128-reference part of K2's column grid (flag-only update path,
+// DESIGN.md section 4): fp32 cosine against the references of that part plus the row's (at most two) tracked candidates outside
+// it; first occurrence of the maximum.  One warp per record, LANE PER REFERENCE (four references per lane, the candidate row
+// broadcast from shared memory): no shuffles until the final argmax merge.  Every lane streams its own reference rows,
+// which are L2-resident.
+constexpr int kPartRefs = 128;          // == kTileN / 2 of ffr_filter_mma.cu (one epilogue warp's columns of a reference tile)
+
+__device__ __forceinline__ void
+recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
+                    float thr, int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
+                    float* __restrict__ best_val, const RecheckLists& lists, float band_tol, int32_t* band_count,
+                    int64_t* band_rows, int64_t band_cap, bool vec) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* c_smem = s_rows + static_cast<size_t>(w) * dim;
+    int64_t count = lists.hdr->part_count;
+    if (count > lists.rec_cap) count = lists.rec_cap;
+    const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
+    for (int64_t k = warp; k < count; k += nwarps) {
+        const RecheckRec rec = lists.recs[lists.rec_cap - 1 - k];
+        const float* c = cand + static_cast<int64_t>(rec.row) * dim;
+        float cc = 0.f;
+        __syncwarp();
+        for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+        __syncwarp();
+        const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
+        // this lane's references: part_base + lane + 32 j (j < 4), plus (lanes 0 and 1) one tracked candidate outside the part
+        constexpr int kR = kPartRefs / 32 + 1;
+        int64_t ri[kR];
+#pragma unroll
+        for (int j = 0; j < kR - 1; ++j) {
+            const int64_t i = static_cast<int64_t>(rec.idx1) + lane + 32 * j;
+            ri[j] = i < n_ref ? i : -1;
+        }
+        ri[kR - 1] = lane == 0 ? rec.idx2 : (lane == 1 ? rec.idx3 : -1);
+        float a[kR], b[kR];
+#pragma unroll
+        for (int j = 0; j < kR; ++j) { a[j] = 0.f; b[j] = 0.f; }
+        if (vec) {
+            const float4* c4 = reinterpret_cast<const float4*>(c_smem);
+            for (int q = 0; q < (dim >> 2); ++q) {
+                const float4 cv = c4[q];
+                float4 rv[kR];
+#pragma unroll
+                for (int j = 0; j < kR; ++j)
+                    rv[j] = ri[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(ref + ri[j] * dim) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < kR; ++j) {
+                    a[j] = fmaf(cv.x, rv[j].x, a[j]); a[j] = fmaf(cv.y, rv[j].y, a[j]);
+                    a[j] = fmaf(cv.z, rv[j].z, a[j]); a[j] = fmaf(cv.w, rv[j].w, a[j]);
+                    b[j] = fmaf(rv[j].x, rv[j].x, b[j]); b[j] = fmaf(rv[j].y, rv[j].y, b[j]);
+                    b[j] = fmaf(rv[j].z, rv[j].z, b[j]); b[j] = fmaf(rv[j].w, rv[j].w, b[j]);
+                }
+            }
+        } else {
+            for (int q = 0; q < dim; ++q) {
+                const float cv = c_smem[q];
+#pragma unroll
+                for (int j = 0; j < kR; ++j) {
+                    const float rv = ri[j] >= 0 ? __ldg(ref + ri[j] * dim + q) : 0.f;
+                    a[j] = fmaf(cv, rv, a[j]);
+                    b[j] = fmaf(rv, rv, b[j]);
+                }
+            }
+        }
+        // NOTE: the accumulation order differs from cos_fp32's lane-strided one by fp32 summation noise only (<= ~1e-7); the
+        // decision between references that close is fp32-ill-defined anyway (tests: TIE_EPS)
+        unsigned long long key = 0ull;
+#pragma unroll
+        for (int j = 0; j < kR; ++j) {
+            if (ri[j] >= 0) {
+                const float sc = __fdiv_rn(a[j], __fmul_rn(__fsqrt_rn(b[j]), cc_sqrt));
+                const unsigned long long kj = pack_key(sc, static_cast<int32_t>(ri[j]));
+                key = kj > key ? kj : key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane == 0) {
+            float v;
+            int32_t bi;
+            unpack_key(key, v, bi);
+            if (key == 0ull) { v = -INFINITY; bi = 0; }
+            emit_result(rec.row, v, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count, band_rows, band_cap);
+        }
+    }
+}
+
 // Work items are (group of kFullGroup flagged rows, slice of kSliceRefs references), handed out round-robin over a
 // fixed grid (the flagged-row count only exists on the device); n_slices slices merge into one result per row.
 constexpr int kSliceRefs = 1024;
@@ -294,6 +385,8 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     pdl_wait();                 // launched as K2's programmatic dependent: everything below reads K2's lists and outputs
     recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
+                        band_rows, band_cap, kVec);
+    recheck_parts_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
                         band_rows, band_cap, kVec);
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
