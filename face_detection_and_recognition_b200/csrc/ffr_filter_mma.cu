@@ -410,6 +410,90 @@ struct KParams {
     unsigned long long* prof;      // optional [gridDim.x][32] stall-cycle counters (diagnostics)
 };
 
+// End of a candidate tile, once per row (the two column halves merged): write keep / index / score and append rows that need
+// fp32 attention to K3's lists (warp-aggregated; the whole warp must call this together):
+//   * near-tie / near-threshold rows with at most three candidates         -> pair records (front of `recs`)
+//   * un-inserted in-window columns confined to ONE 128-reference part      -> part records (back of `recs`)
+//   * a fourth score or hidden columns of a second part inside the window   -> full rescan list
+__device__ __forceinline__ void emit_row(const KParams& p, const Top3& t, const Hidden& hid, int64_t row, int lane) {
+    const bool valid = row < p.n_cand;
+    const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
+    const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
+    // un-inserted columns may be inside the window: of ONE part (K3 rescans its 128 references), or of more
+    const bool hid2 = hid.amb2 > -INFINITY && hid.amb2 >= t.b1 - p.delta;
+    const bool hid1 = hid.amb > -INFINITY && hid.amb >= t.b1 - p.delta;
+    const bool hidden = hid1 || hid2;
+    const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hidden);
+    const bool full = flagged && (hid2 || t.b1 - t.b4 <= p.delta);     // four or more inside the window, or hidden ones anywhere: full rescan
+    const bool part = flagged && !full && hid1;                        // hidden columns in one known part
+    if (valid) {
+        p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
+        p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
+        if (p.best_val != nullptr) p.best_val[row] = t.b1;
+        if (p.band_count != nullptr && fabsf(t.b1 - p.thr) <= p.band_tol) {     // (no re-check: fp16-operand score)
+            const int32_t slot = atomicAdd(p.band_count, 1);
+            if (p.band_rows != nullptr && slot < p.band_cap) p.band_rows[slot] = row;
+        }
+    }
+    const bool pair = flagged && !full && !part;
+    const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
+    const uint32_t umask = __ballot_sync(0xffffffffu, full);
+    const uint32_t qmask = __ballot_sync(0xffffffffu, part);
+    if (qmask != 0) {                                  // part-rescan records grow DOWN from the end of the record array
+        int32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->part_count, __popc(qmask));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (part) {
+            // a row is in exactly one list, so the two ends of the array never meet.  The part's own placeholder entry
+            // (and anything else inside the part) is covered by the part scan; at most two tracked candidates lie outside
+            const int64_t slot = p.lists.rec_cap - 1 - (slot0 + __popc(qmask & ((1u << lane) - 1)));
+            const auto outside = [&](float b, int32_t i) {
+                return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / 2);
+            };
+            int32_t e[2] = {-1, -1};
+            int ne = 0;
+            if (outside(t.b1, t.i1)) e[ne++] = t.i1;
+            if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
+            if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
+            RecheckRec r;
+            r.row = static_cast<int32_t>(row);
+            r.idx1 = hid.base;
+            r.idx2 = e[0];
+            r.idx3 = e[1];
+            if (slot >= 0) p.lists.recs[slot] = r;
+        }
+    }
+    if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
+        int32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->recheck_count, __popc(pmask));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (pair) {
+            const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
+            if (slot < p.lists.rec_cap) {
+                RecheckRec r;
+                r.row = static_cast<int32_t>(row);
+                r.idx1 = t.i1;
+                r.idx2 = near_tie ? t.i2 : -1;
+                r.idx3 = (near_tie && t.i3 >= 0 && t.b1 - t.b3 <= p.delta) ? t.i3 : -1;
+                p.lists.recs[slot] = r;
+            }
+        }
+    }
+    if (umask != 0) {                                  // ... and to the full-rescan list
+        int32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->full_count, __popc(umask));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (full) {
+            const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
+            if (slot < p.lists.full_cap) {
+                p.lists.full_rows[slot] = static_cast<int32_t>(row);
+                p.lists.full_keys[slot] = 0ull;
+                if (slot % kFullGroup == 0) p.lists.full_ctr[slot / kFullGroup] = 0;
+            }
+        }
+    }
+}
+
 // kCG: tcgen05 cta_group (1|2).  Eight epilogue warps = 4 TMEM lane quadrants x 2 column halves.
 // kNormMode != 0 (kNorm): K1 for the candidates runs INSIDE this kernel.  Two extra "normaliser" warps (the hardware allocates warps in
 // fours, so 10 warps cost 12 anyway) read the fp32 rows of the CTA's NEXT candidate tile, L2-normalise them exactly like K1
@@ -450,10 +534,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     uint64_t* t_empty = t_full + 2;
     uint64_t* s_full = t_empty + 2;
     uint64_t* s_empty = s_full + kMaxSBufs;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + kMaxSBufs);
+    uint64_t* m_full = s_empty + kMaxSBufs;                          // stage32: both column halves of a candidate tile have parked their state
+    uint64_t* m_empty = m_full + 2;                                  // stage32: ... and the helper warps have merged + emitted it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_empty + 2);
     uint32_t* norm_count = tmem_slot + 1;                            // kNorm: [2] candidate tiles finished by each normaliser warp
     uint32_t* cons_count = tmem_slot + 3;                            // kNorm: candidate tiles whose A loads have been issued
-    float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [kParts - 1][7][kTileM]
+    float* merge = reinterpret_cast<float*>(extra + kBarrierBytes);  // [10][kTileM]; stage32: [2 slots][2 halves][10][kTileM]
 
     unsigned long long ts_entry = 0;
     if (prof_on != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_entry));
@@ -473,6 +559,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
         // stage32: A tiles are completed by the normaliser warps of BOTH CTAs (one arrive per warp) instead of TMA bytes
         for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], st32 ? 2 * kCG : 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kMaxSBufs; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&m_full[i], kEW); mbar_init(&m_empty[i], 2); }
         norm_count[0] = 0; norm_count[1] = 0; *cons_count = 0;
         for (int i = 0; i < kMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kEW * kCG); }
@@ -679,9 +766,45 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const bool pr = prof_on != nullptr && nw == 0;
             const long long t_nv_begin = clock64();
             uint32_t as = 0, aph = 0, n_done = 0;
-            unsigned long long w_ae = 0, w_sf = 0;
+            unsigned long long w_ae = 0, w_sf = 0, c_merge = 0;
             uint32_t g_buf = static_cast<uint32_t>(nw);                                   // staging buffers are numbered in load order
             const uint32_t sw = (static_cast<uint32_t>(lane) & 7u) << 4;                  // this row's swizzle term
+            // ---- the epilogue's tail, run here: candidate tile u of this CTA (its state parked by the eight epilogue warps in
+            // slot u & 1): each helper warp takes 64 rows, two per lane; merge the column halves (ties -> smaller index), emit.
+            bool k1_waited = false;
+            auto merge_tile = [&](uint32_t u) {
+                const long long tm0 = pr ? clock64() : 0;
+                if (!k1_waited) { pdl_wait(); k1_waited = true; }          // the list counters emit_row appends to are zeroed by K1
+                const uint32_t slot = u & 1u;
+                mbar_wait(&m_full[slot], (u >> 1) & 1u);
+                const int64_t tile_u = tile0 + static_cast<int64_t>(u) * tile_stride;
+#pragma unroll 1
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = nw * 64 + rr * 32 + lane;
+                    const float* ma = merge + (slot * 2 + 0) * 10 * kTileM;
+                    const float* mb = merge + (slot * 2 + 1) * 10 * kTileM;
+                    Top3 t;
+                    Hidden hid;
+                    t.b1 = ma[0 * kTileM + r]; t.b2 = ma[1 * kTileM + r]; t.b3 = ma[2 * kTileM + r]; t.b4 = ma[3 * kTileM + r];
+                    t.i1 = __float_as_int(ma[4 * kTileM + r]); t.i2 = __float_as_int(ma[5 * kTileM + r]); t.i3 = __float_as_int(ma[6 * kTileM + r]);
+                    hid.amb = ma[7 * kTileM + r]; hid.amb2 = ma[8 * kTileM + r]; hid.base = __float_as_int(ma[9 * kTileM + r]);
+                    const float o1 = mb[0 * kTileM + r], o2 = mb[1 * kTileM + r], o3 = mb[2 * kTileM + r], o4 = mb[3 * kTileM + r];
+                    const int32_t j1 = __float_as_int(mb[4 * kTileM + r]), j2 = __float_as_int(mb[5 * kTileM + r]), j3 = __float_as_int(mb[6 * kTileM + r]);
+                    const float o_amb = mb[7 * kTileM + r], o_amb2 = mb[8 * kTileM + r];
+                    const int32_t o_base = __float_as_int(mb[9 * kTileM + r]);
+                    hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
+                    hid.base = o_amb > hid.amb ? o_base : hid.base;
+                    hid.amb = fmaxf(hid.amb, o_amb);
+                    if (o1 != -INFINITY) top3_merge_insert(t, o1, j1);
+                    if (j2 >= 0) top3_merge_insert(t, o2, j2);
+                    if (j3 >= 0) top3_merge_insert(t, o3, j3);
+                    t.b4 = fmaxf(t.b4, o4);
+                    emit_row(p, t, hid, tile_u * (kTileM * kCG) + cta_rank * kTileM + r, lane);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&m_empty[slot]);
+                if (pr) c_merge += static_cast<unsigned long long>(clock64() - tm0);
+            };
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
                 const int64_t row0 = tile * (kTileM * kCG) + cta_rank * kTileM;
                 mbar_wait_timed(&a_empty[as], aph ^ 1, pr, w_ae);                          // A stage free again
@@ -690,49 +813,48 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     const uint32_t sph = (g_buf / static_cast<uint32_t>(p.s_bufs)) & 1u;
                     mbar_wait_timed(&s_full[sb], sph, pr, w_sf);
                     const uint8_t* src = smem_s + sb * kStageBytes + lane * 128;
-                    // COMPACT loops (eight iterations of four float4 each): fully unrolled, this pass was 10 KB of code that shared
-                    // an instruction cache with the epilogue's hot loop -- both crawled at ~7 cycles per instruction.
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll 1
-                    for (int g = (p.norm_diag & 1) ? 4 : 0; g < 4; ++g) {
+                    // ONE pass with the whole row (128 floats) in registers: 32 LDS.128 issued back to back, the sum of squares
+                    // in four interleaved chains (not warp_sum's tree: the fp16 rows can differ from the other forms' by one fp16
+                    // ulp in rare elements, like x * (1/|x|) differs from K1's x / |x|), one IEEE sqrt + division, then 16 STS.128.
+                    // (Round 1 read every row twice in compact loops to keep the code small; with the tail's work moved into these
+                    // warps their time per tile matters, and half the shared-memory reads is what pays.)
+                    float4 x[32];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
                         const uint8_t* sg = src + g * (kStageBytes / 4);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 x0 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 0) << 4) ^ sw));
-                            const float4 x1 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 1) << 4) ^ sw));
-                            const float4 x2 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 2) << 4) ^ sw));
-                            const float4 x3 = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(4 * h + 3) << 4) ^ sw));
-                            q0 = fmaf(x0.x, x0.x, q0); q0 = fmaf(x0.y, x0.y, q0); q0 = fmaf(x0.z, x0.z, q0); q0 = fmaf(x0.w, x0.w, q0);
-                            q1 = fmaf(x1.x, x1.x, q1); q1 = fmaf(x1.y, x1.y, q1); q1 = fmaf(x1.z, x1.z, q1); q1 = fmaf(x1.w, x1.w, q1);
-                            q2 = fmaf(x2.x, x2.x, q2); q2 = fmaf(x2.y, x2.y, q2); q2 = fmaf(x2.z, x2.z, q2); q2 = fmaf(x2.w, x2.w, q2);
-                            q3 = fmaf(x3.x, x3.x, q3); q3 = fmaf(x3.y, x3.y, q3); q3 = fmaf(x3.z, x3.z, q3); q3 = fmaf(x3.w, x3.w, q3);
-                        }
+                        for (int c = 0; c < 8; ++c)
+                            x[g * 8 + c] = (p.norm_diag & 1) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                             : *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(c) << 4) ^ sw));
+                    }
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        q0 = fmaf(x[c].x, x[c].x, q0); q0 = fmaf(x[c].y, x[c].y, q0); q0 = fmaf(x[c].z, x[c].z, q0); q0 = fmaf(x[c].w, x[c].w, q0);
+                        q1 = fmaf(x[c + 1].x, x[c + 1].x, q1); q1 = fmaf(x[c + 1].y, x[c + 1].y, q1); q1 = fmaf(x[c + 1].z, x[c + 1].z, q1); q1 = fmaf(x[c + 1].w, x[c + 1].w, q1);
+                        q2 = fmaf(x[c + 2].x, x[c + 2].x, q2); q2 = fmaf(x[c + 2].y, x[c + 2].y, q2); q2 = fmaf(x[c + 2].z, x[c + 2].z, q2); q2 = fmaf(x[c + 2].w, x[c + 2].w, q2);
+                        q3 = fmaf(x[c + 3].x, x[c + 3].x, q3); q3 = fmaf(x[c + 3].y, x[c + 3].y, q3); q3 = fmaf(x[c + 3].z, x[c + 3].z, q3); q3 = fmaf(x[c + 3].w, x[c + 3].w, q3);
                     }
                     const int r = part * kStageRows + lane;                               // row inside the tile
                     // rows past the end stay zero
                     const float inv = (row0 + r < p.n_cand) ? __fdiv_rn(1.0f, sqrtf((q0 + q1) + (q2 + q3))) : 0.f;
                     uint8_t* dst = smem_a + as * a_stage_bytes + r * 128;
-#pragma unroll 1
-                    for (int g = (p.norm_diag & 2) ? 4 : 0; g < 4; ++g) {                 // 32 input floats -> 4 chunks of 8 halves
-                        const uint8_t* sg = src + g * (kStageBytes / 4);
-                        uint8_t* dg = dst + (g >> 1) * kABlockBytes;
-                        // all eight loads first: behind a store to shared memory the compiler will not hoist the next loads
-                        // (same address space), and each pair then waited out its own ~35-cycle latency
-                        float4 x[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(c) << 4) ^ sw));
+                    for (int g = 0; g < 4; ++g) {                                         // 32 input floats -> 4 chunks of 8 halves
+                        uint8_t* dg = dst + (g >> 1) * kABlockBytes;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const __half2 h0 = __floats2half2_rn(x[2 * c].x * inv, x[2 * c].y * inv);
-                            const __half2 h1 = __floats2half2_rn(x[2 * c].z * inv, x[2 * c].w * inv);
-                            const __half2 h2 = __floats2half2_rn(x[2 * c + 1].x * inv, x[2 * c + 1].y * inv);
-                            const __half2 h3 = __floats2half2_rn(x[2 * c + 1].z * inv, x[2 * c + 1].w * inv);
+                            const float4 lo = x[g * 8 + 2 * c], hi = x[g * 8 + 2 * c + 1];
+                            const __half2 h0 = __floats2half2_rn(lo.x * inv, lo.y * inv);
+                            const __half2 h1 = __floats2half2_rn(lo.z * inv, lo.w * inv);
+                            const __half2 h2 = __floats2half2_rn(hi.x * inv, hi.y * inv);
+                            const __half2 h3 = __floats2half2_rn(hi.z * inv, hi.w * inv);
                             uint4 pk;
                             pk.x = *reinterpret_cast<const uint32_t*>(&h0);
                             pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                             pk.z = *reinterpret_cast<const uint32_t*>(&h2);
                             pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(dg + ((static_cast<uint32_t>(4 * (g & 1) + c) << 4) ^ sw)) = pk;
+                            if (!(p.norm_diag & 2)) *reinterpret_cast<uint4*>(dg + ((static_cast<uint32_t>(4 * (g & 1) + c) << 4) ^ sw)) = pk;
                         }
                     }
                     __syncwarp();
@@ -744,14 +866,19 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (kCG == 2 && !leader) mbar_arrive_leader_cta(&a_full[as]);
                     else                     mbar_arrive(&a_full[as]);
                 }
+                // the A tile of candidate tile n_done is on its way to the tensor core; candidate tile n_done - 2 finished its
+                // epilogue a whole tile ago: merge + emit it now, while the MMAs of tile n_done - 1 run
+                if (n_done >= 2u) merge_tile(n_done - 2u);
                 ++n_done;
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
+            for (uint32_t u = n_done >= 2u ? n_done - 2u : 0u; u < n_done; ++u) merge_tile(u);     // drain: the last two tiles
             if (pr && lane == 0) {
                 p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
                 p.prof[blockIdx.x * 32 + 14] = n_done;
                 p.prof[blockIdx.x * 32 + 18] = w_ae;
                 p.prof[blockIdx.x * 32 + 19] = w_sf;
+                p.prof[blockIdx.x * 32 + 20] = c_merge;
             }
         } else {
         const int nvec = p.dim >> 2;                                   // float4 per row (dim % 4 == 0 checked on the host)
@@ -946,6 +1073,28 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // warps of ONE lane quadrant (ids 1+q / 5+q, alternating with the tile parity so that an early arrive for tile
             // n + 2 cannot complete tile n's barrier); with CTA-wide barriers every quadrant waited for the slowest warp.
             const long long t_tail0 = pr ? clock64() : 0;
+            if constexpr (st32) {
+                // stage32: the tail is NOT run here.  Merging the two column halves, classifying the row and appending to K3's
+                // lists is ~300 dependent instructions that used to stall this warp for as long as a reference tile's hot loop
+                // (with four reference tiles per candidate tile -- BASELINE configs[1] -- a fifth of the epilogue's time).  Both
+                // halves park their state in one of two shared-memory slots and go on with the next candidate tile; the two
+                // normaliser warps (helpers), which have spare time at every reference-set size, merge and emit it.
+                const uint32_t slot = c_it & 1u;
+                mbar_wait(&m_empty[slot], ((c_it >> 1) & 1u) ^ 1u);          // merged two candidate tiles ago: free again
+                float* mg = merge + (slot * 2 + h) * 10 * kTileM;
+                mg[0 * kTileM + r_in_tile] = t.b1;
+                mg[1 * kTileM + r_in_tile] = t.b2;
+                mg[2 * kTileM + r_in_tile] = t.b3;
+                mg[3 * kTileM + r_in_tile] = t.b4;
+                mg[4 * kTileM + r_in_tile] = __int_as_float(t.i1);
+                mg[5 * kTileM + r_in_tile] = __int_as_float(t.i2);
+                mg[6 * kTileM + r_in_tile] = __int_as_float(t.i3);
+                mg[7 * kTileM + r_in_tile] = hid.amb;
+                mg[8 * kTileM + r_in_tile] = hid.amb2;
+                mg[9 * kTileM + r_in_tile] = __int_as_float(hid.base);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&m_full[slot]);                  // (release at CTA scope: the warp's stores above)
+            } else {
             if (first_tile) pdl_wait();                          // the re-check header the appends below count in is zeroed by K1
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
@@ -993,83 +1142,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     t.b4 = fmaxf(t.b4, ob[pp][3]);
                 }
 
-                const bool valid = row < p.n_cand;
-                const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
-                const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
-                // un-inserted columns may be inside the window: of ONE part (K3 rescans its 128 references), or of more
-                const bool hid2 = hid.amb2 > -INFINITY && hid.amb2 >= t.b1 - p.delta;
-                const bool hid1 = hid.amb > -INFINITY && hid.amb >= t.b1 - p.delta;
-                const bool hidden = hid1 || hid2;
-                const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hidden);
-                const bool full = flagged && (hid2 || t.b1 - t.b4 <= p.delta);     // four or more inside the window, or hidden ones anywhere: full rescan
-                const bool part = flagged && !full && hid1;                        // hidden columns in one known part
-                if (valid) {
-                    p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
-                    p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
-                    if (p.best_val != nullptr) p.best_val[row] = t.b1;
-                    if (p.band_count != nullptr && fabsf(t.b1 - p.thr) <= p.band_tol) {     // (no re-check: fp16-operand score)
-                        const int32_t slot = atomicAdd(p.band_count, 1);
-                        if (p.band_rows != nullptr && slot < p.band_cap) p.band_rows[slot] = row;
-                    }
-                }
-                const bool pair = flagged && !full && !part;
-                const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
-                const uint32_t umask = __ballot_sync(0xffffffffu, full);
-                const uint32_t qmask = __ballot_sync(0xffffffffu, part);
-                if (qmask != 0) {                                  // part-rescan records grow DOWN from the end of the record array
-                    int32_t slot0 = 0;
-                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->part_count, __popc(qmask));
-                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                    if (part) {
-                        // a row is in exactly one list, so the two ends of the array never meet.  The part's own placeholder entry
-                        // (and anything else inside the part) is covered by the part scan; at most two tracked candidates lie outside
-                        const int64_t slot = p.lists.rec_cap - 1 - (slot0 + __popc(qmask & ((1u << lane) - 1)));
-                        const auto outside = [&](float b, int32_t i) {
-                            return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / kParts);
-                        };
-                        int32_t e[2] = {-1, -1};
-                        int ne = 0;
-                        if (outside(t.b1, t.i1)) e[ne++] = t.i1;
-                        if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
-                        if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
-                        RecheckRec r;
-                        r.row = static_cast<int32_t>(row);
-                        r.idx1 = hid.base;
-                        r.idx2 = e[0];
-                        r.idx3 = e[1];
-                        if (slot >= 0) p.lists.recs[slot] = r;
-                    }
-                }
-                if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
-                    int32_t slot0 = 0;
-                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->recheck_count, __popc(pmask));
-                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                    if (pair) {
-                        const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
-                        if (slot < p.lists.rec_cap) {
-                            RecheckRec r;
-                            r.row = static_cast<int32_t>(row);
-                            r.idx1 = t.i1;
-                            r.idx2 = near_tie ? t.i2 : -1;
-                            r.idx3 = (near_tie && t.i3 >= 0 && t.b1 - t.b3 <= p.delta) ? t.i3 : -1;
-                            p.lists.recs[slot] = r;
-                        }
-                    }
-                }
-                if (umask != 0) {                                  // ... and to the full-rescan list
-                    int32_t slot0 = 0;
-                    if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->full_count, __popc(umask));
-                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                    if (full) {
-                        const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
-                        if (slot < p.lists.full_cap) {
-                            p.lists.full_rows[slot] = static_cast<int32_t>(row);
-                            p.lists.full_keys[slot] = 0ull;
-                            if (slot % kFullGroup == 0) p.lists.full_ctr[slot / kFullGroup] = 0;
-                        }
-                    }
-                }
+                emit_row(p, t, hid, row, lane);
             }
+            }   // !st32
             first_tile = false;
             ++c_it;
             if (pr) c_tail += static_cast<unsigned long long>(clock64() - t_tail0);
@@ -1219,11 +1294,11 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     if (a_stages < 1) a_stages = 1;
     if (a_stages > kMaxAStages) a_stages = kMaxAStages;
     constexpr int ew = 8;                                  // epilogue warps: 4 TMEM lane quadrants x 2 column halves
-    const uint32_t extra = kBarrierBytes + (ew / 4 - 1) * kMergeBytes;
     // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
-    // MMAs read the other), the B ring gets what is left (>= 2 stages)
+    // MMAs read the other), the B ring gets what is left (>= 2 stages); the tail's hand-over buffer is two slots x two halves
     const bool st32 = fuse && filter_mma_stage32_ok(dim, dim_pad);
-    int s_bufs = st32 ? kMaxSBufs : 0;
+    const uint32_t extra = kBarrierBytes + (st32 ? 4 : 1) * kMergeBytes;
+    int s_bufs = st32 ? kMaxSBufs - 1 : 0;                 // five 16 KB staging buffers leave three B stages beside the merge slots
     if (st32) {
         a_stages = 2;
         while (s_bufs > 3 && kSmemLimit - extra - s_bufs * kStageBytes < a_stages * a_stage + 2 * b_stage) --s_bufs;

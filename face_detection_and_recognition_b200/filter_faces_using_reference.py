@@ -115,18 +115,78 @@ def _embed_paths(model, paths: List[str], batch_size: int) -> np.ndarray:
     return np.concatenate(outs, axis=0) if outs else np.zeros((0, 0), dtype=np.float32)
 
 
-def _embed_paths_device(model, paths: List[str], batch_size: int, device: torch.device) -> torch.Tensor:
+# ---- embedding producer on the GPU -------------------------------------------------------------
+# The reference decodes, resizes and standardises one image at a time on the host (tf.io.decode_jpeg -> tf.image.resize ->
+# per_image_standardization, :60-68), embeds the references with batch size 1 (:77-84) and hands every batch to the model
+# as a NumPy array (:168-184).  Here a model that can take CUDA tensors (``embed``) is fed from a device-side pipeline:
+# file bytes are read by a small thread pool, the whole batch is decoded by nvJPEG in one call
+# (torchvision.io.decode_jpeg(device=cuda)), resize + standardisation run on the GPU, the next batch's files are read while
+# the model works on the current one, and the embeddings go to the filter without leaving the device.
+
+def preprocess_decoded_device(imgs: List[torch.Tensor], in_size: Tuple[int, int] = (160, 160)) -> torch.Tensor:
+    """uint8 [3, H, W] CUDA images (any sizes) -> [B, h, w, 3] float32: [0, 1] scaling, bilinear resize (no antialias,
+    half-pixel centres: what tf.image.resize / read_and_preprocess_img do), per-image standardisation
+    ``(x - mean) / max(std, 1/sqrt(N))``.  Images of equal size are resized in one call."""
+    h, w = in_size
+    out = torch.empty((len(imgs), 3, h, w), dtype=torch.float32, device=imgs[0].device)
+    groups = {}
+    for i, im in enumerate(imgs):
+        groups.setdefault(tuple(im.shape[-2:]), []).append(i)
+    for shape, idxs in groups.items():
+        x = torch.stack([imgs[i] for i in idxs]).to(torch.float32).div_(255.0)
+        if shape != (h, w):
+            x = torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear", align_corners=False, antialias=False)
+        out[torch.as_tensor(idxs, device=out.device)] = x
+    n = out[0].numel()
+    mean = out.mean(dim=(1, 2, 3), keepdim=True)
+    std = out.var(dim=(1, 2, 3), unbiased=False, keepdim=True).sqrt_()
+    out = (out - mean) / torch.clamp(std, min=1.0 / float(np.sqrt(n)))
+    return out.permute(0, 2, 3, 1).contiguous()
+
+
+def read_and_preprocess_batch_device(paths: List[str], device: torch.device, in_size: Tuple[int, int] = (160, 160),
+                                     datas: List[torch.Tensor] = None) -> torch.Tensor:
+    """``read_and_preprocess_img`` for a whole batch on the GPU: one batched nvJPEG decode + GPU resize / standardise.
+    ``datas`` = the files' bytes if the caller has already read them (prefetch)."""
+    from torchvision.io import ImageReadMode, decode_jpeg, read_file
+    if datas is None:
+        datas = [read_file(p) for p in paths]
+    imgs = decode_jpeg(datas, mode=ImageReadMode.RGB, device=device)
+    return preprocess_decoded_device(imgs, in_size)
+
+
+def _embed_paths_device(model, paths: List[str], batch_size: int, device: torch.device,
+                        in_size: Tuple[int, int] = (160, 160), stats: dict = None) -> torch.Tensor:
     """Embeddings as a float32 CUDA tensor.  A model that offers ``embed(batch) -> CUDA tensor`` (MobileFaceNetModel)
-    keeps them on the device: pinned host batch -> async H2D -> forward -> straight into the filter, no NumPy round
-    trip (the reference goes device -> NumPy -> Python loop per row, :184-189).  Any other model goes through
-    ``predict`` (the reference's contract)."""
-    if not hasattr(model, "embed"):
-        return torch.from_numpy(_embed_paths(model, paths, batch_size)).to(device)
+    is fed by the device-side pipeline above and its output goes straight into the filter: no PIL, no NumPy round trip
+    (the reference goes device -> NumPy -> Python loop per row, :184-189).  Any other model goes through ``predict``
+    (the reference's contract).  ``stats`` (optional dict) receives ``{"images", "seconds", "decoder"}``."""
+    import time
+    t0 = time.perf_counter()
+    if not hasattr(model, "embed") or device.type != "cuda":
+        out = torch.from_numpy(_embed_paths(model, paths, batch_size)).to(device)
+        if stats is not None:
+            stats.update(images=len(paths), seconds=time.perf_counter() - t0, decoder="PIL (host)")
+        return out
+    from concurrent.futures import ThreadPoolExecutor
+    from torchvision.io import read_file
     outs = []
-    for s in range(0, len(paths), batch_size):
-        batch = torch.stack([read_and_preprocess_img(p) for p in paths[s:s + batch_size]]).pin_memory()
-        outs.append(model.embed(batch.to(device, non_blocking=True)).float())
-    return torch.cat(outs, dim=0) if outs else torch.zeros((0, 0), dtype=torch.float32, device=device)
+    chunks = [paths[s:s + batch_size] for s in range(0, len(paths), batch_size)]
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        def read_chunk(chunk):
+            return list(pool.map(read_file, chunk))
+        with ThreadPoolExecutor(max_workers=1) as ahead:         # the NEXT batch's file reads overlap this batch's GPU work
+            nxt = ahead.submit(read_chunk, chunks[0]) if chunks else None
+            for k, chunk in enumerate(chunks):
+                datas = nxt.result()
+                nxt = ahead.submit(read_chunk, chunks[k + 1]) if k + 1 < len(chunks) else None
+                batch = read_and_preprocess_batch_device(chunk, device, in_size, datas=datas)
+                outs.append(model.embed(batch).float())
+    out = torch.cat(outs, dim=0) if outs else torch.zeros((0, 0), dtype=torch.float32, device=device)
+    if stats is not None:
+        torch.cuda.synchronize(device)
+        stats.update(images=len(paths), seconds=time.perf_counter() - t0, decoder="nvJPEG (torchvision.io.decode_jpeg, device)")
+    return out
 
 
 def get_ref_mean_vec_and_thres_from_imgs(model, ref_class_path: str,
@@ -216,7 +276,8 @@ def all_ref_stats(model, ref_class_paths: List[str], ref_img_per_class: int, dev
     feats, counts = [], []
     for path in ref_class_paths:
         imgs = sorted(glob.glob(path + "/*.jpg"))[:ref_img_per_class]
-        f = _embed_paths_device(model, imgs, 1, dev)                 # batch 1 like the reference (:77)
+        # the reference embeds its references with batch size 1 (:77); a device-side model takes them as ONE batch
+        f = _embed_paths_device(model, imgs, max(1, len(imgs)) if hasattr(model, "embed") else 1, dev)
         print(f"Calculating ref mean vector for {path}")
         print(f"number of samples considered for reference={len(imgs)}", f"ref mean shape={(1, f.shape[1]) if len(imgs) else None}",
               f"ref feat shape={(len(imgs), 1, f.shape[1] if len(imgs) else 0)}")

@@ -126,7 +126,8 @@ def prof(n_ref, n_cand, dim, easy=False, bench_data=False, flags=None):
               f"CTA entry spread {(ent.max() - ent.min()).item() / 1e3:.2f} us; first entry -> last exit {(b[:, 9].max() - ent.min()).item() / 1e3:.2f} us", flush=True)
     if m[13] > 0:
         print(f"    normaliser 0: total {m[13]:.3e} cyc for {m[14]:.0f} candidate tiles ({m[13] / max(m[14], 1):.0f} per tile); "
-              f"stage32: waiting for the A stage {m[18] / m[13]:.1%}, for staged fp32 rows {m[19] / m[13]:.1%}", flush=True)
+              f"stage32: waiting for the A stage {m[18] / m[13]:.1%}, for staged fp32 rows {m[19] / m[13]:.1%}, "
+              f"merge + emit of finished tiles {m[20] / m[13]:.1%} ({m[20] / max(m[14], 1):.0f} cyc per tile)", flush=True)
 
 
 if __name__ == "__main__":
