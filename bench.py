@@ -13,7 +13,7 @@ Workloads (BASELINE.json configs): the default, cfg3, is the per-GPU shard of co
 candidates x 512-d, candidate-sharded over 8 GPUs -> 1.25M candidates per GPU, weak scaling: at --gpus 8 the job IS
 configs[3]); cfg1 = configs[1] (1k x 100k x 128), cfg2 = configs[2] (10k x 1M x 512), cfg4 = per-GPU shard of
 configs[4] (100k x 1.25M x 128); cfg3_full = configs[3] on ONE GPU (10k x 10M x 512, 20.5 GB), the strong-scaling
-denominator; dup8 = cfg3's shape with a duplicate-heavy gallery (every identity enrolled 8 times).
+denominator; dup8 / near8 = cfg3's shape with a duplicate-heavy gallery (every identity enrolled 8 times).
 
 What the line carries beyond the contract: ``verified`` (every rank checks a >= 10 k-row sample of what it timed against
 the CPU oracle, and at N > 1 that rank r's slice of the gathered result is rank r's local result), ``secondary`` (short
@@ -48,9 +48,13 @@ WORKLOADS = {
     "cfg4": dict(n_ref=100_000, n_cand=1_250_000, dim=128, adv_every=1250, n_dup=80,
                  name="configs[4] per-GPU shard: 100k ref x 1.25M cand x 128-d (10M candidates over 8 GPUs)"),
     # duplicate-heavy gallery (the realistic case for face data): 1250 identities, each enrolled 8 times -- 4 exact copies
-    # (the same photo enrolled again) and 4 near-identical ones (cos >= 0.9999 to the first)
-    "dup8": dict(n_ref=10_000, n_cand=1_250_000, dim=512, adv_every=1250, n_dup=0, dup_group=8,
-                 name="duplicate-heavy gallery: 1250 identities x 8 enrolments (4 exact + 4 near-identical) x 1.25M cand x 512-d"),
+    # (the same photo enrolled again) and 4 other photos of the same person (cos 0.9 to the first)
+    "dup8": dict(n_ref=10_000, n_cand=1_250_000, dim=512, adv_every=1250, n_dup=0, dup_group=8, sib_cos=0.9,
+                 name="duplicate-heavy gallery: 1250 identities x 8 enrolments (4 exact copies + 4 other photos, cos 0.9) x 1.25M cand x 512-d"),
+    # the pathological variant: the 4 other enrolments are near-identical too (cos 0.99995: inside the fp16 window), so every
+    # candidate has >= 5 leaders that only fp32 can tell apart -- K3's part rescan decides all of them
+    "near8": dict(n_ref=10_000, n_cand=1_250_000, dim=512, adv_every=1250, n_dup=0, dup_group=8, sib_cos=0.99995,
+                  name="near-identical gallery: 1250 identities x 8 enrolments (4 exact copies + 4 at cos 0.99995) x 1.25M cand x 512-d"),
     # the reference's literal mode (filter_faces_using_reference.py:186-189) at scale: ONE mean vector, Euclid keep test.
     # 0.5 FLOP/byte: the HBM-bound end of the path (exact fp32 streaming kernel K2s, no tensor cores)
     "n1": dict(n_ref=1, n_cand=10_000_000, dim=128, metric="euclid", thr=1.2, adv_every=0, n_dup=0,
@@ -92,8 +96,8 @@ def config_of(w, world):
 def make_refs(w, device):
     """Unit-norm references, seed 42 (the reference's seed, filter_faces...:24).  ``n_dup`` rows of the second half are
     exact copies of rows of the first half (exact ties -> first-argmax rule); ``dup_group`` = G builds a
-    duplicate-heavy gallery instead: identities of G consecutive rows, rows 1..G/2-1 exact copies of row 0, the rest
-    near-identical (cos ~ 0.99995)."""
+    duplicate-heavy gallery instead: identities of G consecutive rows, rows 1..G/2-1 exact copies of row 0, the rest at
+    cosine ``sib_cos`` to it (0.9: other photos of the person; 0.99995: near-identical)."""
     import torch
     n_ref, dim = w["n_ref"], w["dim"]
     g = torch.Generator(device=device).manual_seed(42)
@@ -111,7 +115,10 @@ def make_refs(w, device):
         out = base.repeat_interleave(grp, dim=0)
         k = torch.arange(ids * grp, device=device) % grp
         near = (k >= grp // 2)[:, None]
-        out = torch.where(near, torch.nn.functional.normalize(out + 0.01 * jit[:ids * grp]), out)
+        c = float(w.get("sib_cos", 0.9))
+        j = jit[:ids * grp]
+        j = torch.nn.functional.normalize(j - (j * out).sum(1, keepdim=True) * out)
+        out = torch.where(near, torch.nn.functional.normalize(c * out + (1 - c * c) ** 0.5 * j), out)
         ref[:ids * grp] = out
     return ref
 

@@ -114,7 +114,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t hdr, ref16, cand16, recs, full_rows, full_keys, full_ctr, total;
+    size_t hdr, ref16, cand16, recs, full_rows, full_keys, full_ctr, dedup, total;
     bool mma;
 };
 
@@ -128,7 +128,7 @@ bool mma_eligible(int64_t n_ref, int32_t dim, int metric, int flags) {
 
 // need_c16: the fp16 copy of the candidates lives in the workspace (false for fp16 input and for stage32, whose fp16 A
 // tiles only ever exist in shared memory: 320 MB less at BASELINE configs[4]'s shard)
-WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool mma, bool need_c16) {
+WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool mma, bool need_c16, bool dedup) {
     WsLayout L{};
     L.mma = mma;
     size_t off = 0;
@@ -141,6 +141,7 @@ WsLayout ws_layout(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, bool m
         L.full_rows = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(int32_t), 256);
         L.full_keys = off; off += align_up(static_cast<size_t>(n_cand) * sizeof(unsigned long long), 256);
         L.full_ctr = off;  off += align_up((static_cast<size_t>(n_cand) / kFullGroup + 1) * sizeof(int32_t), 256);
+        L.dedup = off;     if (dedup && dtype == FFR_DTYPE_F32) off += align_up(dedup_workspace_bytes(n_ref, static_cast<int32_t>(ld)), 256);
     }
     L.total = off;
     return L;
@@ -161,7 +162,10 @@ int check_common(const void* ref, int64_t n_ref, const void* cand, int64_t n_can
 }
 
 // core: ref16_pre != nullptr -> references already normalised/converted (ctx pipeline caches them)
-int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim,
+// ref16_pre != nullptr: the caller already holds the prepared references (fp16, normalised; when map_pre / nuniq_pre are given:
+// exact duplicates folded, see ffr_dedup.cu)
+int filter_core(const void* ref, const __half* ref16_pre, const int32_t* map_pre, const int32_t* nuniq_pre, int64_t n_ref,
+                const void* cand, int64_t n_cand, int32_t dim,
                 int dtype, int metric, float thr, int64_t ref_index_base, uint8_t* keep, int32_t* best_idx,
                 float* best_val, float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, int flags,
                 void* workspace, size_t ws_bytes, cudaStream_t s) {
@@ -175,7 +179,8 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     const bool fuse = mma && dtype == FFR_DTYPE_F32 && n_cand > 0 &&
                       filter_mma_can_fuse(static_cast<const float*>(cand), n_ref, n_cand, dim, ld);
     const bool need_c16 = !(fuse && filter_mma_skips_cand16(n_ref, n_cand, dim));
-    const WsLayout L = ws_layout(ref16_pre ? 0 : n_ref, n_cand, dim, dtype, mma, need_c16);
+    const bool dedup = mma && dtype == FFR_DTYPE_F32 && ref16_pre == nullptr && dedup_wanted(n_ref, n_cand);
+    const WsLayout L = ws_layout(ref16_pre ? 0 : n_ref, n_cand, dim, dtype, mma, need_c16, dedup);
     if (workspace == nullptr || ws_bytes < L.total) {
         set_error("workspace too small: need %zu bytes, got %zu%s", L.total, workspace ? ws_bytes : (size_t)0,
                   (mma && dtype == FFR_DTYPE_F32 && need_c16 && (reinterpret_cast<uintptr_t>(cand) & 15) != 0)
@@ -225,6 +230,14 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
         ++launches;
         if (r16 != nullptr) ref16 = r16;
         cand16 = c16;
+        if (dedup) {                       // fold bit-identical reference rows: K2 scans the unique ones and maps its columns back
+            __half* r16c = nullptr;
+            int32_t *map = nullptr, *nuniq = nullptr;
+            rc = launch_dedup_refs(static_cast<const float*>(ref), r16, n_ref, dim, ld, ws + L.dedup, &r16c, &map, &nuniq, s);
+            if (rc != FFR_OK) return rc;
+            launches += 4;
+            ref16 = r16c; map_pre = map; nuniq_pre = nuniq;
+        }
     } else {
         if (ref16 == nullptr) ref16 = static_cast<const __half*>(ref);
         cand16 = const_cast<__half*>(static_cast<const __half*>(cand));      // fp16 input: only read
@@ -245,13 +258,13 @@ int filter_core(const void* ref, const __half* ref16_pre, int64_t n_ref, const v
     if (g_ev_k2_begin != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_begin, s));
     rc = launch_filter_mma(ref16, n_ref, cand16, fuse_cand, dim, n_cand, ld, thr, delta, thr_band, ref_index_base, keep, best_idx,
                            best_val, lists, recheck ? 0 : 1, band_tol, band_count, band_rows, band_cap,
-                           /*after_k1=*/dtype == FFR_DTYPE_F32, s);
+                           /*after_k1=*/dtype == FFR_DTYPE_F32 && !dedup, map_pre, nuniq_pre, s);
     if (rc != FFR_OK) return rc;
     if (g_ev_k2_end != nullptr) FFR_CUDA_TRY(cudaEventRecord(g_ev_k2_end, s));
     if (recheck) {
         rc = launch_recheck(static_cast<const float*>(ref), n_ref, static_cast<const float*>(cand), n_cand, dim, nullptr,
                             nullptr, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol,
-                            band_count, band_rows, band_cap, s);
+                            band_count, band_rows, band_cap, map_pre, nuniq_pre, s);
         if (rc != FFR_OK) return rc;
     }
     return FFR_OK;
@@ -309,7 +322,7 @@ size_t ffr_filter_workspace_bytes(int64_t n_ref, int64_t n_cand, int32_t dim, in
     // sized for the tcgen05 path whenever it could be chosen (including FFR_FLAG_FORCE_MMA)
     const bool mma = metric == FFR_METRIC_COSINE && dim <= 512;
     const bool need_c16 = !(mma && dtype == FFR_DTYPE_F32 && filter_mma_skips_cand16(n_ref, n_cand, dim));
-    return ws_layout(n_ref, n_cand, dim, dtype, mma, need_c16).total;
+    return ws_layout(n_ref, n_cand, dim, dtype, mma, need_c16, mma && dedup_wanted(n_ref, n_cand)).total;
 }
 
 int ffr_filter_ex(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype,
@@ -321,7 +334,7 @@ int ffr_filter_ex(const void* ref, int64_t n_ref, const void* cand, int64_t n_ca
     int rc = check_common(ref, n_ref, cand, n_cand, dim, dtype, metric, keep, best_idx);
     if (rc != FFR_OK) return rc;
     if (ffr_device_count() == 0) { set_error("no CUDA device"); return FFR_ERR_CUDA; }
-    return filter_core(ref, nullptr, n_ref, cand, n_cand, dim, dtype, metric, thr, ref_index_base, keep, best_idx,
+    return filter_core(ref, nullptr, nullptr, nullptr, n_ref, cand, n_cand, dim, dtype, metric, thr, ref_index_base, keep, best_idx,
                        best_val, band_tol, band_count, band_rows, band_cap, flags, workspace, ws_bytes,
                        static_cast<cudaStream_t>(stream));
 }
@@ -343,7 +356,8 @@ int ffr_filter_stats(const void* workspace, int64_t out[8], ffr_stream_t stream)
     out[2] = g_last.ws == workspace ? g_last.path : -1;
     out[3] = g_last.ws == workspace ? g_last.launches : -1;
     out[4] = h.part_count;
-    out[5] = out[6] = out[7] = 0;
+    out[5] = h.refs_scanned;
+    out[6] = out[7] = 0;
     return FFR_OK;
 }
 
@@ -412,6 +426,7 @@ struct ffr_ctx {
     cudaEvent_t ev_h2d[2], ev_done[2];
     float* d_ref;
     __half* d_ref16;
+    void* d_dedup;             // scratch of the duplicate-reference fold (per call, not per chunk)
     float* d_cand[2];
     uint8_t* d_keep[2];
     int32_t* d_idx[2];
@@ -428,7 +443,7 @@ void ffr_ctx_destroy(ffr_ctx* c) {
     cudaSetDevice(c->device);
     if (c->s_comp) cudaStreamSynchronize(c->s_comp);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
-    cudaFree(c->d_ref); cudaFree(c->d_ref16);
+    cudaFree(c->d_ref); cudaFree(c->d_ref16); cudaFree(c->d_dedup);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->d_cand[i]); cudaFree(c->d_keep[i]); cudaFree(c->d_idx[i]); cudaFree(c->d_val[i]); cudaFree(c->ws[i]);
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
@@ -454,7 +469,8 @@ int ffr_ctx_create(int device, int64_t max_ref, int64_t chunk_cand, int32_t max_
     const size_t ld = static_cast<size_t>(ffr_padded_dim(max_dim));
     FFR_CTX_TRY(cudaMalloc(&c->d_ref, static_cast<size_t>(max_ref) * max_dim * sizeof(float)));
     FFR_CTX_TRY(cudaMalloc(&c->d_ref16, static_cast<size_t>(max_ref) * ld * 2));
-    c->ws_bytes = ws_layout(1, chunk_cand, max_dim <= 512 ? max_dim : 512, FFR_DTYPE_F32, true, true).total;   // any dim <= max_dim
+    FFR_CTX_TRY(cudaMalloc(&c->d_dedup, dedup_workspace_bytes(max_ref, static_cast<int32_t>(ld))));
+    c->ws_bytes = ws_layout(1, chunk_cand, max_dim <= 512 ? max_dim : 512, FFR_DTYPE_F32, true, true, false).total;   // any dim <= max_dim
     if (c->ws_bytes < 4096) c->ws_bytes = 4096;
     for (int i = 0; i < 2; ++i) {
         FFR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
@@ -482,10 +498,18 @@ int ffr_ctx_filter_host(ffr_ctx* c, const float* ref, int64_t n_ref, const float
     const bool mma = mma_eligible(n_ref, dim, metric, flags);
     FFR_CUDA_TRY(cudaMemcpyAsync(c->d_ref, ref, static_cast<size_t>(n_ref) * dim * sizeof(float), cudaMemcpyHostToDevice, c->s_comp));
     const __half* ref16 = nullptr;
-    if (mma) {      // references are normalised / converted once, not per chunk
+    const int32_t *ref_map = nullptr, *n_unique = nullptr;
+    if (mma) {      // references are normalised / converted (and exact duplicates folded) once, not per chunk
         rc = launch_l2norm(c->d_ref, n_ref, dim, c->d_ref16, ffr_padded_dim(dim), nullptr, nullptr, c->s_comp);
         if (rc != FFR_OK) return rc;
         ref16 = c->d_ref16;
+        if (dedup_wanted(n_ref, n_cand)) {
+            __half* r16c = nullptr;
+            int32_t *map = nullptr, *nuniq = nullptr;
+            rc = launch_dedup_refs(c->d_ref, c->d_ref16, n_ref, dim, ffr_padded_dim(dim), c->d_dedup, &r16c, &map, &nuniq, c->s_comp);
+            if (rc != FFR_OK) return rc;
+            ref16 = r16c; ref_map = map; n_unique = nuniq;
+        }
     }
     int64_t i = 0;
     for (int64_t off = 0; off < n_cand; off += c->chunk, ++i) {
@@ -496,7 +520,7 @@ int ffr_ctx_filter_host(ffr_ctx* c, const float* ref, int64_t n_ref, const float
                                      cudaMemcpyHostToDevice, c->s_copy));
         FFR_CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->s_copy));
         FFR_CUDA_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_h2d[b], 0));
-        rc = filter_core(c->d_ref, ref16, n_ref, c->d_cand[b], m, dim, FFR_DTYPE_F32, metric, thr, ref_index_base,
+        rc = filter_core(c->d_ref, ref16, ref_map, n_unique, n_ref, c->d_cand[b], m, dim, FFR_DTYPE_F32, metric, thr, ref_index_base,
                          c->d_keep[b], c->d_idx[b], c->d_val[b], 0.f, nullptr, nullptr, 0, flags, c->ws[b], c->ws_bytes,
                          c->s_comp);
         if (rc != FFR_OK) return rc;

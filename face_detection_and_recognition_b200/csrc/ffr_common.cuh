@@ -75,7 +75,8 @@ struct WsHeader {
     int32_t path;            // 0 fp32, 1 mma
     int32_t launches;
     int32_t part_count;      // rows whose hidden columns all lie in one 128-reference part (records at the END of recs, growing down)
-    int32_t pad[59];
+    int32_t refs_scanned;    // reference rows K2 actually scanned (< n_ref when exact duplicates were folded)
+    int32_t pad[58];
 };
 
 // ---- device helpers -------------------------------------------------------------------------------
@@ -294,13 +295,19 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const 
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
-                      int64_t band_cap, bool after_k1, cudaStream_t s);
+                      int64_t band_cap, bool after_k1, const int32_t* ref_map, const int32_t* n_ref_dev, cudaStream_t s);
+// exact-duplicate reference rows folded before K2 (ffr_dedup.cu)
+bool dedup_wanted(int64_t n_ref, int64_t n_cand);
+size_t dedup_workspace_bytes(int64_t n_ref, int32_t ld);
+int launch_dedup_refs(const float* ref32, const __half* ref16_full, int64_t n_ref, int32_t dim, int32_t ld, void* ws,
+                      __half** out_ref16, int32_t** out_map, int32_t** out_n_unique_dev, cudaStream_t s);
 bool filter_mma_skips_cand16(int64_t n_ref, int64_t n_cand, int32_t dim);
 void get_last_k2_config(int out[8]);
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
                    const float* ref_norm, const float* cand_norm, float thr, int64_t ref_index_base,
                    uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
-                   float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s);
+                   float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap,
+                   const int32_t* ref_map, const int32_t* n_unique_dev, cudaStream_t s);
 int launch_ref_stats_batched(const float* ref_feat, const int32_t* offsets, int32_t n_classes, int32_t dim, float* mean,
                              float* thres, cudaStream_t s);
 int launch_first_match_stream(float* g_feat, float* g_bbox, int32_t* g_count, int32_t cap, const float* queries,

@@ -376,7 +376,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 struct KParams {
-    int64_t n_ref, n_cand;
+    int64_t n_ref, n_cand;          // n_ref: rows of the fp16 reference matrix the tensor map describes
+    const int32_t* n_ref_dev;      // duplicate references folded (ffr_dedup.cu): the number of UNIQUE rows, known on the device only;
+    const int32_t* ref_map;        // ... rows [*n_ref_dev, n_ref) are stale, and column i stands for original reference ref_map[i]
     int32_t kb_count, a_stages, b_stages;
     float thr, delta, thr_band;
     int64_t ref_index_base;
@@ -410,87 +412,104 @@ struct KParams {
     unsigned long long* prof;      // optional [gridDim.x][32] stall-cycle counters (diagnostics)
 };
 
-// End of a candidate tile, once per row (the two column halves merged): write keep / index / score and append rows that need
-// fp32 attention to K3's lists (warp-aggregated; the whole warp must call this together):
-//   * near-tie / near-threshold rows with at most three candidates         -> pair records (front of `recs`)
-//   * un-inserted in-window columns confined to ONE 128-reference part      -> part records (back of `recs`)
-//   * a fourth score or hidden columns of a second part inside the window   -> full rescan list
-__device__ __forceinline__ void emit_row(const KParams& p, const Top3& t, const Hidden& hid, int64_t row, int lane) {
+// End of a candidate tile, once per row (the two column halves merged): classify_row writes keep / index / score and decides
+// which of K3's lists the row goes to; append_rows adds the rows of a warp (kNR per lane) to the lists, warp-aggregated, with
+// at most ONE atomic per list and all of them in flight together (a returning global atomic is ~700 cycles: one per list and
+// row, one after the other, was most of the tail's time).  The whole warp must call append_rows together.
+//   1 pair : near-tie / near-threshold row with at most three candidates       -> pair record (front of `recs`)
+//   2 part : un-inserted in-window columns confined to ONE 128-reference part   -> part record (back of `recs`)
+//   3 full : a fourth score or hidden columns of a second part inside the window -> full rescan list
+struct RowOut {
+    int cls;
+    RecheckRec rec;
+};
+
+__device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, const Hidden& hid, int64_t row) {
+    RowOut o;
     const bool valid = row < p.n_cand;
     const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
     const bool near_thr = fabsf(t.b1 - p.thr) <= p.thr_band;
     // un-inserted columns may be inside the window: of ONE part (K3 rescans its 128 references), or of more
     const bool hid2 = hid.amb2 > -INFINITY && hid.amb2 >= t.b1 - p.delta;
     const bool hid1 = hid.amb > -INFINITY && hid.amb >= t.b1 - p.delta;
-    const bool hidden = hid1 || hid2;
-    const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hidden);
-    const bool full = flagged && (hid2 || t.b1 - t.b4 <= p.delta);     // four or more inside the window, or hidden ones anywhere: full rescan
+    const bool flagged = valid && !p.no_recheck && (near_tie || near_thr || hid1 || hid2);
+    const bool full = flagged && (hid2 || t.b1 - t.b4 <= p.delta);     // four or more inside the window, or hidden ones anywhere
     const bool part = flagged && !full && hid1;                        // hidden columns in one known part
+    const int32_t* map = p.ref_map;                                     // duplicate references folded: compact -> original index
+    const auto orig = [&](int32_t i) { return (map != nullptr && i >= 0) ? map[i] : i; };
     if (valid) {
         p.keep[row] = (t.b1 >= p.thr) ? 1 : 0;
-        p.best_idx[row] = static_cast<int32_t>(t.i1 + p.ref_index_base);
+        p.best_idx[row] = static_cast<int32_t>(orig(t.i1) + p.ref_index_base);
         if (p.best_val != nullptr) p.best_val[row] = t.b1;
         if (p.band_count != nullptr && fabsf(t.b1 - p.thr) <= p.band_tol) {     // (no re-check: fp16-operand score)
             const int32_t slot = atomicAdd(p.band_count, 1);
             if (p.band_rows != nullptr && slot < p.band_cap) p.band_rows[slot] = row;
         }
     }
-    const bool pair = flagged && !full && !part;
-    const uint32_t pmask = __ballot_sync(0xffffffffu, pair);
-    const uint32_t umask = __ballot_sync(0xffffffffu, full);
-    const uint32_t qmask = __ballot_sync(0xffffffffu, part);
-    if (qmask != 0) {                                  // part-rescan records grow DOWN from the end of the record array
-        int32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->part_count, __popc(qmask));
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (part) {
-            // a row is in exactly one list, so the two ends of the array never meet.  The part's own placeholder entry
-            // (and anything else inside the part) is covered by the part scan; at most two tracked candidates lie outside
-            const int64_t slot = p.lists.rec_cap - 1 - (slot0 + __popc(qmask & ((1u << lane) - 1)));
-            const auto outside = [&](float b, int32_t i) {
-                return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / 2);
-            };
-            int32_t e[2] = {-1, -1};
-            int ne = 0;
-            if (outside(t.b1, t.i1)) e[ne++] = t.i1;
-            if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
-            if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
-            RecheckRec r;
-            r.row = static_cast<int32_t>(row);
-            r.idx1 = hid.base;
-            r.idx2 = e[0];
-            r.idx3 = e[1];
-            if (slot >= 0) p.lists.recs[slot] = r;
-        }
+    o.cls = !flagged ? 0 : (full ? 3 : (part ? 2 : 1));
+    o.rec.row = static_cast<int32_t>(row);
+    o.rec.idx1 = o.rec.idx2 = o.rec.idx3 = -1;
+    if (o.cls == 2) {
+        // The part's own placeholder entry (and anything else inside the part) is covered by K3's scan of the part; at most two
+        // tracked candidates lie outside it.  The part is named by its first COMPACT column; the candidates by original index.
+        const auto outside = [&](float b, int32_t i) {
+            return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / 2);
+        };
+        int32_t e[2] = {-1, -1};
+        int ne = 0;
+        if (outside(t.b1, t.i1)) e[ne++] = t.i1;
+        if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
+        if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
+        o.rec.idx1 = hid.base;
+        o.rec.idx2 = orig(e[0]);
+        o.rec.idx3 = orig(e[1]);
+    } else if (o.cls == 1) {
+        o.rec.idx1 = orig(t.i1);
+        o.rec.idx2 = near_tie ? orig(t.i2) : -1;
+        o.rec.idx3 = (near_tie && t.i3 >= 0 && t.b1 - t.b3 <= p.delta) ? orig(t.i3) : -1;
     }
-    if (pmask != 0) {                                  // warp-aggregated append to the two-candidate list
-        int32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->recheck_count, __popc(pmask));
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (pair) {
-            const int64_t slot = slot0 + __popc(pmask & ((1u << lane) - 1));
-            if (slot < p.lists.rec_cap) {
-                RecheckRec r;
-                r.row = static_cast<int32_t>(row);
-                r.idx1 = t.i1;
-                r.idx2 = near_tie ? t.i2 : -1;
-                r.idx3 = (near_tie && t.i3 >= 0 && t.b1 - t.b3 <= p.delta) ? t.i3 : -1;
-                p.lists.recs[slot] = r;
-            }
+    return o;
+}
+
+template <int kNR>
+__device__ __forceinline__ void append_rows(const KParams& p, const RowOut (&o)[kNR], int lane) {
+    uint32_t m[3][kNR];
+    int tot[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kNR; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            m[l][k] = __ballot_sync(0xffffffffu, o[k].cls == l + 1);
+            tot[l] += __popc(m[l][k]);
         }
+    if ((tot[0] | tot[1] | tot[2]) == 0) return;
+    int32_t base[3] = {0, 0, 0};
+    if (lane == 0) {                                   // the (up to three) atomics go out back to back
+        if (tot[0] != 0) base[0] = atomicAdd(&p.lists.hdr->recheck_count, tot[0]);
+        if (tot[1] != 0) base[1] = atomicAdd(&p.lists.hdr->part_count, tot[1]);
+        if (tot[2] != 0) base[2] = atomicAdd(&p.lists.hdr->full_count, tot[2]);
     }
-    if (umask != 0) {                                  // ... and to the full-rescan list
-        int32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(&p.lists.hdr->full_count, __popc(umask));
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (full) {
-            const int64_t slot = slot0 + __popc(umask & ((1u << lane) - 1));
+#pragma unroll
+    for (int l = 0; l < 3; ++l) base[l] = __shfl_sync(0xffffffffu, base[l], 0);
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kNR; ++k) {
+        if (o[k].cls == 1) {                           // pair records grow UP from the front of the record array ...
+            const int64_t slot = base[0] + __popc(m[0][k] & lt);
+            if (slot < p.lists.rec_cap) p.lists.recs[slot] = o[k].rec;
+        } else if (o[k].cls == 2) {                    // ... part records DOWN from its end: a row is in exactly one list
+            const int64_t slot = p.lists.rec_cap - 1 - (base[1] + __popc(m[1][k] & lt));
+            if (slot >= 0) p.lists.recs[slot] = o[k].rec;
+        } else if (o[k].cls == 3) {
+            const int64_t slot = base[2] + __popc(m[2][k] & lt);
             if (slot < p.lists.full_cap) {
-                p.lists.full_rows[slot] = static_cast<int32_t>(row);
+                p.lists.full_rows[slot] = o[k].rec.row;
                 p.lists.full_keys[slot] = 0ull;
                 if (slot % kFullGroup == 0) p.lists.full_ctr[slot / kFullGroup] = 0;
             }
         }
+#pragma unroll
+        for (int l = 0; l < 3; ++l) base[l] += __popc(m[l][k]);
     }
 }
 
@@ -549,7 +568,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     const bool leader = cta_rank == 0;
     const int64_t n_tiles = (p.n_cand + kTileM * kCG - 1) / (kTileM * kCG);   // tiles of the CTA pair
     const int64_t tile0 = blockIdx.x / kCG, tile_stride = gridDim.x / kCG;
-    const int32_t n_rt = static_cast<int32_t>((p.n_ref + kAccN - 1) / kAccN);
+    // duplicate references folded: the live row count is a device-side value written by the dedup kernels, which precede this
+    // launch in plain stream order (the kernel is then NOT launched as K1's programmatic dependent)
+    const int64_t n_ref = p.n_ref_dev != nullptr ? static_cast<int64_t>(__ldg(p.n_ref_dev)) : p.n_ref;
+    const int32_t n_rt = static_cast<int32_t>((n_ref + kAccN - 1) / kAccN);
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -708,7 +730,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (kCG == 1) {                             // tail reference tile: only as many columns as needed
                         // (the cta_group::2 analogue -- N = 2 * ceil16(live) when the live references sit in CTA 0's half --
                         // is correct but did not pay: an N = 32 MMA costs ~100 cycles, and the same-box wall clock got worse)
-                        const int64_t ncols = p.n_ref - static_cast<int64_t>(rt) * kAccN;
+                        const int64_t ncols = n_ref - static_cast<int64_t>(rt) * kAccN;
                         if (ncols < kAccN) idesc = umma_idesc_f16(kTileM * kCG, static_cast<uint32_t>((ncols + 15) & ~int64_t(15)));
                     }
                     const uint32_t d_tmem = tmem_base + acc * kAccN;
@@ -774,11 +796,16 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             bool k1_waited = false;
             auto merge_tile = [&](uint32_t u) {
                 const long long tm0 = pr ? clock64() : 0;
-                if (!k1_waited) { pdl_wait(); k1_waited = true; }          // the list counters emit_row appends to are zeroed by K1
+                if (!k1_waited) {                                          // the list counters append_rows counts in are zeroed by K1
+                    pdl_wait();
+                    k1_waited = true;
+                    if (blockIdx.x == 0 && nw == 0 && lane == 0) p.lists.hdr->refs_scanned = static_cast<int32_t>(n_ref);
+                }
                 const uint32_t slot = u & 1u;
                 mbar_wait(&m_full[slot], (u >> 1) & 1u);
                 const int64_t tile_u = tile0 + static_cast<int64_t>(u) * tile_stride;
-#pragma unroll 1
+                RowOut ro[2];
+#pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int r = nw * 64 + rr * 32 + lane;
                     const float* ma = merge + (slot * 2 + 0) * 10 * kTileM;
@@ -799,10 +826,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (j2 >= 0) top3_merge_insert(t, o2, j2);
                     if (j3 >= 0) top3_merge_insert(t, o3, j3);
                     t.b4 = fmaxf(t.b4, o4);
-                    emit_row(p, t, hid, tile_u * (kTileM * kCG) + cta_rank * kTileM + r, lane);
+                    ro[rr] = classify_row(p, t, hid, tile_u * (kTileM * kCG) + cta_rank * kTileM + r);
                 }
+                // the slot's contents are in registers: hand it back before the list appends (their atomics are the slow part)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&m_empty[slot]);
+                append_rows<2>(p, ro, lane);
                 if (pr) c_merge += static_cast<unsigned long long>(clock64() - tm0);
             };
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -995,7 +1024,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 const long long tp0 = pr ? clock64() : 0;
                 tc_fence_after();
                 const int32_t col0 = rt * kAccN;
-                const int64_t ncols64 = p.n_ref - static_cast<int64_t>(col0);
+                const int64_t ncols64 = n_ref - static_cast<int64_t>(col0);
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccN + h * (kChunksPerPart * 32);
                 const int32_t base0 = col0 + h * (kChunksPerPart * 32);
                 if (hot_ok) {
@@ -1095,7 +1124,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&m_full[slot]);                  // (release at CTA scope: the warp's stores above)
             } else {
-            if (first_tile) pdl_wait();                          // the re-check header the appends below count in is zeroed by K1
+            if (first_tile) {
+                pdl_wait();                                      // the re-check header the appends below count in is zeroed by K1
+                if (blockIdx.x == 0 && threadIdx.x == 64) p.lists.hdr->refs_scanned = static_cast<int32_t>(n_ref);
+            }
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
             if (!merger) {
@@ -1142,7 +1174,9 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     t.b4 = fmaxf(t.b4, ob[pp][3]);
                 }
 
-                emit_row(p, t, hid, row, lane);
+                RowOut ro[1];
+                ro[0] = classify_row(p, t, hid, row);
+                append_rows<1>(p, ro, lane);
             }
             }   // !st32
             first_tile = false;
@@ -1270,7 +1304,8 @@ struct BandArgs { float tol; int32_t* count; int64_t* rows; int64_t cap; };
 int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, const float* cand32, int32_t dim,
                            int64_t n_cand, int32_t dim_pad,
                            float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
-                           RecheckLists lists, int no_recheck, BandArgs band, float* dbg_scores, bool after_k1, cudaStream_t s) {
+                           RecheckLists lists, int no_recheck, BandArgs band, float* dbg_scores, bool after_k1,
+                           const int32_t* ref_map, const int32_t* n_ref_dev, cudaStream_t s) {
     if (dim_pad % kBlockK != 0 || dim_pad < kBlockK || dim_pad > 512) {
         set_error("filter_mma: padded dim %d not in {64..512 step 64}", dim_pad);
         return FFR_ERR_UNSUPPORTED;
@@ -1331,7 +1366,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
 
     unsigned long long* const prof = g_prof.load(std::memory_order_relaxed);
     KParams p;
-    p.n_ref = n_ref; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
+    p.n_ref = n_ref; p.n_ref_dev = n_ref_dev; p.ref_map = ref_map; p.n_cand = n_cand; p.kb_count = kb; p.a_stages = a_stages; p.b_stages = b_stages;
     p.thr = thr; p.delta = delta; p.thr_band = thr_band; p.ref_index_base = ref_index_base;
     p.keep = keep; p.best_idx = idx; p.best_val = val; p.lists = lists; p.no_recheck = no_recheck; p.dbg_scores = dbg_scores; p.prof = prof; p.epi_mode = kn.epi_mode;
     p.band_tol = band.tol; p.band_count = no_recheck ? band.count : nullptr; p.band_rows = band.rows; p.band_cap = band.cap;
@@ -1402,7 +1437,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (after_k1 && kn.pdl != 0) {       // the previous launch of this stream is K1 (it triggers its dependents at entry)
+    if (after_k1 && n_ref_dev == nullptr && kn.pdl != 0) {   // the previous launch of this stream is K1 (it triggers its dependents at entry)
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;
@@ -1437,10 +1472,10 @@ int launch_filter_mma(const __half* ref16, int64_t n_ref, __half* cand16, const 
                       int64_t n_cand, int32_t dim_pad,
                       float thr, float delta, float thr_band, int64_t ref_index_base, uint8_t* keep, int32_t* idx, float* val,
                       RecheckLists lists, int no_recheck, float band_tol, int32_t* band_count, int64_t* band_rows,
-                      int64_t band_cap, bool after_k1, cudaStream_t s) {
+                      int64_t band_cap, bool after_k1, const int32_t* ref_map, const int32_t* n_ref_dev, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, cand16, cand32, dim, n_cand, dim_pad, thr, delta, thr_band, ref_index_base,
                                   keep, idx, val, lists, no_recheck, BandArgs{band_tol, band_count, band_rows, band_cap}, nullptr,
-                                  after_k1, s);
+                                  after_k1, ref_map, n_ref_dev, s);
 }
 
 // true when the fused schedule needs NO fp16 copy of the candidates in the workspace (stage32: the fp16 A tiles only ever
@@ -1462,7 +1497,7 @@ int launch_filter_mma_debug(const __half* ref16, int64_t n_ref, const __half* ca
                             float thr, float delta, uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
                             float* scores, cudaStream_t s) {
     return launch_filter_mma_impl(ref16, n_ref, const_cast<__half*>(cand16), nullptr, dim_pad, n_cand, dim_pad, thr, delta, delta, 0, keep, idx,
-                                  val, lists, 0, BandArgs{0.f, nullptr, nullptr, 0}, scores, false, s);
+                                  val, lists, 0, BandArgs{0.f, nullptr, nullptr, 0}, scores, false, nullptr, nullptr, s);
 }
 
 }  // namespace ffr

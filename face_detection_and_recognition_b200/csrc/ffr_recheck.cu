@@ -204,9 +204,12 @@ __device__ __forceinline__ void
 recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
                     float thr, int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
                     float* __restrict__ best_val, const RecheckLists& lists, float band_tol, int32_t* band_count,
-                    int64_t* band_rows, int64_t band_cap, bool vec) {
+                    int64_t* band_rows, int64_t band_cap, bool vec, const int32_t* __restrict__ ref_map,
+                    const int32_t* __restrict__ n_unique_dev) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* c_smem = s_rows + static_cast<size_t>(w) * dim;
+    // duplicate references folded before K2: the part is a range of COMPACT columns (ref_map: column -> original reference)
+    const int64_t n_cols = n_unique_dev != nullptr ? static_cast<int64_t>(__ldg(n_unique_dev)) : n_ref;
     int64_t count = lists.hdr->part_count;
     if (count > lists.rec_cap) count = lists.rec_cap;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
@@ -225,7 +228,7 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
 #pragma unroll
         for (int j = 0; j < kR - 1; ++j) {
             const int64_t i = static_cast<int64_t>(rec.idx1) + lane + 32 * j;
-            ri[j] = i < n_ref ? i : -1;
+            ri[j] = i < n_cols ? (ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + i)) : i) : -1;
         }
         ri[kR - 1] = lane == 0 ? rec.idx2 : (lane == 1 ? rec.idx3 : -1);
         float a[kR], b[kR];
@@ -383,11 +386,12 @@ rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, 
 // One launch re-checks everything K2 flagged: phase A = K3a (pairs list), phase B = K3b (full-rescan list; small or
 // tiled walk, chosen from the device-side count, uniform over the grid).  The phases touch disjoint rows.
 template <bool kVec>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)      // two CTAs per SM (<= 128 registers): the fixed grid of 2 x SMs is ONE wave
 recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim, float thr,
                int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
                float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
-               int64_t* band_rows, int64_t band_cap) {
+               int64_t* band_rows, int64_t band_cap, const int32_t* __restrict__ ref_map,
+               const int32_t* __restrict__ n_unique_dev) {
     extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows | staged reference tile
     __shared__ float s_ccs[kFullGroup];
     __shared__ unsigned long long s_key[kWarps][kFullGroup];
@@ -397,7 +401,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
     recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
                         band_rows, band_cap, kVec);
     recheck_parts_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
-                        band_rows, band_cap, kVec);
+                        band_rows, band_cap, kVec, ref_map, n_unique_dev);
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
     if (count == 0) return;
@@ -608,7 +612,8 @@ __global__ void unpack_results_kernel(const uint8_t* __restrict__ packed, int64_
 int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n_cand, int32_t dim,
                    const float* /*ref_norm*/, const float* /*cand_norm*/, float thr, int64_t ref_index_base,
                    uint8_t* keep, int32_t* idx, float* val, RecheckLists lists,
-                   float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap, cudaStream_t s) {
+                   float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap,
+                   const int32_t* ref_map, const int32_t* n_unique_dev, cudaStream_t s) {
     if (n_cand == 0) return FFR_OK;
     static_assert(kWarps == kFullGroup, "one warp parks one candidate row of a full-rescan group");
     const int sms = num_sms();
@@ -640,9 +645,9 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     cfg.attrs = attr;
     cfg.numAttrs = knobs().pdl != 0 ? 1 : 0;
     if (vec) FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<true>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                             lists, band_tol, band_count, band_rows, band_cap));
+                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev));
     else     FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<false>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                             lists, band_tol, band_count, band_rows, band_cap));
+                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev));
     FFR_LAUNCH_CHECK("recheck");
     return FFR_OK;
 }

@@ -153,7 +153,7 @@ def face_filter(ref: torch.Tensor, cand: torch.Tensor, thr: float, metric="cosin
             arr = (C.c_int64 * 8)()
             check(lib.ffr_filter_stats(ws.data_ptr(), arr, _stream_ptr(dev)))
             res.stats = {"rechecked": arr[0], "part_rescans": arr[4], "full_rescans": arr[1],
-                         "path": "tcgen05" if arr[2] == 1 else "fp32", "launches": arr[3]}
+                         "path": "tcgen05" if arr[2] == 1 else "fp32", "launches": arr[3], "refs_scanned": arr[5]}
             if arr[2] == 1:
                 cfg = (C.c_int32 * 8)()
                 lib.ffr_debug_last_k2_config(cfg)

@@ -103,7 +103,8 @@ int ffr_filter_ex(const void* ref, int64_t n_ref, const void* cand, int64_t n_ca
 /* statistics of the last ffr_filter* call that used this workspace (device->host copy, synchronises
  * the stream): out[0] = rows re-checked in fp32 against their two or three leading references (near-tie or
  * near-threshold), out[1] = rows that needed the full fp32 rescan, out[2] = path taken (0 fp32 CUDA-core,
- * 1 tcgen05), out[3] = kernels launched, out[4] = rows re-checked against one 128-reference part, out[5..7] = 0. */
+ * 1 tcgen05), out[3] = kernels launched, out[4] = rows re-checked against one 128-reference part, out[5] = reference
+ * rows the tensor-core kernel scanned (< n_ref when bit-identical reference rows were folded), out[6..7] = 0. */
 int ffr_filter_stats(const void* workspace, int64_t out[8], ffr_stream_t stream);
 
 /* ---- K5: reference statistics -----------------------------------------------------------------

@@ -66,7 +66,10 @@ def _make_dataset(root, rng, classes=("alice", "bob", "carol"), n_ref=12, n_cand
                 img = np.clip(pattern + rng.normal(0, 25, pattern.shape), 0, 255).astype(np.uint8)
                 hh, ww = sizes[i % 3]                                            # variable image sizes, like the bundled faces
                 img = np.kron(img[:hh, :ww] if hh <= 24 and ww <= 20 else np.resize(img, (hh, ww, 3)), np.ones((8, 8, 1), dtype=np.uint8))
-                Image.fromarray(img).save(os.path.join(d, f"{i:03d}.jpg"), quality=95)
+                # 4:4:4 (no chroma subsampling): the two decoders then differ by IDCT rounding only; with 4:2:0 their
+                # chroma UPSAMPLING filters differ too (libjpeg's "fancy" triangle filter vs nvJPEG's), which on these
+                # random 8 x 8 colour blocks is a few per cent of the dynamic range at every block edge
+                Image.fromarray(img).save(os.path.join(d, f"{i:03d}.jpg"), quality=95, subsampling=0)
     return os.path.join(root, "unf"), os.path.join(root, "ref")
 
 

@@ -498,3 +498,38 @@ def test_two_devices_in_one_process(ops):
         torch.cuda.synchronize(dev)
         assert res.stats["path"] == "tcgen05"
         assert np.mean(res.best_idx.cpu().numpy() == io) > 0.999
+
+
+# ---------------------------------------------------------------- exact-duplicate references are folded before K2 (round 2)
+@pytest.mark.parametrize("n_ref,n_cand,dim,copies", [(6000, 400_000, 128, 8), (4096, 500_000, 256, 3), (10_000, 210_000, 512, 5)])
+def test_duplicate_heavy_gallery_is_folded(ops, ffr_env, n_ref, n_cand, dim, copies):
+    """A gallery that enrols the same embedding several times (exact copies, scattered over the whole index range): the
+    bit-identical rows are dropped before the tensor-core scan, K2 reports the unique row count, the answers are those of the
+    oracle on the FULL gallery (first occurrence of the maximum), and nothing is left for K3's full rescan -- while the same
+    call with FFR_DEDUP_REFS=0 sends every such row there (the cliff this removes) and gives the same answers."""
+    rng = np.random.default_rng(n_ref + copies)
+    n_id = n_ref // copies
+    base = rng.standard_normal((n_id, dim)).astype(np.float32)
+    ref = np.concatenate([base] * copies + [rng.standard_normal((n_ref - n_id * copies, dim)).astype(np.float32)])
+    perm = rng.permutation(n_ref)
+    ref = ref[perm]                                              # copies land anywhere; first occurrence = smallest index
+    cand = rng.standard_normal((n_cand, dim)).astype(np.float32)
+    hit = rng.integers(0, n_id, n_cand // 2)
+    cand[::2][: len(hit)] = base[hit] + 0.35 * rng.standard_normal((len(hit), dim)).astype(np.float32)
+    sample = rng.choice(n_cand, 3000, replace=False)
+    res = _check_cosine(ops, ref, cand, 0.5, sample=sample)
+    n_unique = len(np.unique(ref, axis=0))
+    assert res.stats["refs_scanned"] == n_unique < n_ref, res.stats
+    assert res.stats["full_rescans"] < n_cand // 200, res.stats
+    ffr_env.setenv("FFR_DEDUP_REFS", "0")
+    dev = torch.device("cuda:0")
+    small = slice(0, 20_000)
+    r0 = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand[small]).to(dev), 0.5, want_stats=True)
+    ffr_env.setenv("FFR_DEDUP_REFS", "1")
+    assert r0.stats["refs_scanned"] == n_ref
+    if copies >= 4:
+        assert r0.stats["full_rescans"] + r0.stats["part_rescans"] > 5000          # every planted row has >= 4 equal leaders
+    r1 = ops.face_filter(torch.from_numpy(ref).to(dev), torch.from_numpy(cand).to(dev), 0.5)
+    gap, _ = _top2_gap64(np.unique(ref, axis=0), cand[small][:2000])
+    ok = torch.from_numpy(gap > TIE_EPS).to(dev)
+    assert torch.equal(r0.best_idx[:2000][ok], r1.best_idx[:2000][ok]) and torch.equal(r0.keep[:2000], r1.keep[:2000])
