@@ -469,7 +469,9 @@ def roofline_of(r, pk, traffic):
         gbs = hbm_bytes / (ms_step * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "filter_fp32_kernel (K2s)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": gbs / pk["hbm"], "peak_source": pk["source"], "bytes_per_launch": hbm_bytes, "traffic": traffic}
-    flops = 2.0 * n_ref * n_cand * dim
+    # FLOPs of the contraction K2 actually ran: bit-identical reference rows are folded before the scan (ffr_dedup.cu)
+    n_scanned = int(r["stats"].get("refs_scanned") or n_ref)
+    flops = 2.0 * n_scanned * n_cand * dim
     ach = flops / (r["k2_ms"] * 1e-3) / 1e12
     ach_step = flops / (ms_step * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "filter_mma_kernel (K2)", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -477,7 +479,7 @@ def roofline_of(r, pk, traffic):
             "frac_of_sustained": ach / pk["tflops_sustained"] if pk["tflops_sustained"] else None,
             "frac_whole_step": ach_step / pk["tflops"],
             "peak_source": pk["source"], "k2_ms": r["k2_ms"], "k2_share_of_step": r["k2_ms"] / ms_step,
-            "flops_per_launch": flops, "traffic": traffic,
+            "flops_per_launch": flops, "refs_scanned": n_scanned, "traffic": traffic,
             "step_hbm": {"algorithmic_bytes": hbm_bytes, "gbs_over_step": hbm_bytes / (ms_step * 1e-3) / 1e9,
                          "frac_of_hbm_peak": hbm_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm"]}}
 
