@@ -37,6 +37,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 
 #include "ffr_common.cuh"
 
@@ -1017,7 +1018,11 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             hid.amb = hid.amb2 = -INFINITY;
             hid.base = 0;
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
-            for (int rt = 0; rt < n_rt; ++rt) {
+            // One reference tile.  The loop over FULL tiles and the one partial last tile are separate copies of this body: the
+            // masking of columns >= n_ref is 260 instructions that the hot loop would otherwise carry (and jump over) on every
+            // tile -- the body is what has to stream through the instruction cache.
+            auto ref_tile = [&](const int rt, auto partial_tag) {
+                constexpr bool kPartial = decltype(partial_tag)::value;
                 const uint32_t acc = p.acc_stages == 2 ? (t_it & 1) : 0u;
                 const uint32_t tph = p.acc_stages == 2 ? ((t_it >> 1) & 1) : (t_it & 1);
                 mbar_wait_timed(&t_full[acc], tph, pr, w_tfull);
@@ -1045,7 +1050,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                         if (kCG == 2 && !leader) mbar_arrive_leader_relaxed(&t_empty[acc]);
                         else                     mbar_arrive(&t_empty[acc]);
                     }
-                    if (ncols64 < kAccN) {                         // partial last reference tile: columns >= n_ref -> -inf
+                    if constexpr (kPartial) {                      // partial last reference tile: columns >= n_ref -> -inf
                         const int n_left = static_cast<int>(ncols64) - h * (kChunksPerPart * 32);
 #pragma unroll
                         for (int cc = 0; cc < kChunksPerPart; ++cc)
@@ -1094,7 +1099,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     if (pr) c_gen += static_cast<unsigned long long>(clock64() - tp0);
                 }
                 ++t_it;
-            }
+            };
+            const int32_t n_full = static_cast<int32_t>(n_ref / kAccN);
+            for (int rt = 0; rt < n_full; ++rt) ref_tile(rt, std::false_type{});
+            if (n_full < n_rt) ref_tile(n_full, std::true_type{});
             // ---- hand the other column part(s) over, merge, emit.  The merging thread runs ~300 dependent instructions
             // alone on its scheduler (its partner is already in the next tile's loads), so with two parts the ROLE alternates
             // from candidate tile to candidate tile: each warp carries the tail every other tile, and since the reader of

@@ -229,6 +229,9 @@ def get_parsed_args(argv=None):
                         default=os.environ.get("FFR_MOBILEFACENET_DIR",
                                                "../face_detection_and_extraction/modules/mobile_facenet"))
     parser.add_argument('--device', type=str, default="cuda:0")
+    parser.add_argument('--ngpus', type=int, default=1,
+                        help='distribute the classes (independent problems, reference :161) over this many GPUs: one worker '
+                             'thread and one model replica per GPU')
     parser.add_argument('--allow_random_init', action='store_true')
     return parser.parse_args(argv)
 
@@ -292,9 +295,13 @@ def all_ref_stats(model, ref_class_paths: List[str], ref_img_per_class: int, dev
     return [(mean[i:i + 1], float(thres_h[i])) for i in range(len(counts))]
 
 
-def main(argv=None, model=None):
+def main(argv=None, model=None, model_factory=None):
+    """``model``: any object with the reference's ``predict`` contract (:84,184); ``model_factory(device) -> model`` builds
+    the per-GPU replicas of ``--ngpus`` > 1 (default: MobileFaceNetModel on that device)."""
     args = get_parsed_args(argv)
     print(args)
+    if model is None and model_factory is not None:
+        model = model_factory(args.device)
     if model is None:
         model = MobileFaceNetModel(args.savedmodel_path, args.mobilefacenet_dir, device=args.device,
                                    allow_random_init=args.allow_random_init)
@@ -319,19 +326,53 @@ def main(argv=None, model=None):
     os.makedirs(clean_dir, exist_ok=True)
     os.makedirs(unclean_dir, exist_ok=True)
 
+    def run_classes(indices, mdl, device, progress=None, say=None):
+        """The reference's per-class loop (:161-199) over ``indices`` on one device; returns {class index: summary line}
+        (``say``: print each line as soon as its class is done, like the reference)."""
+        paths = [ref_class_paths[i] for i in indices]
+        stats = None if args.gallery else all_ref_stats(mdl, paths, args.ref_img_per_class, device)
+        lines = {}
+        for k, i in enumerate(indices):
+            similar_cnt, total, _ = filter_class(mdl, ref_class_paths[i], unfiltered_class_paths[i], clean_dir, unclean_dir,
+                                                 batch_size=args.batch_size, ref_img_per_class=args.ref_img_per_class,
+                                                 gallery=args.gallery, threshold=args.threshold, device=device,
+                                                 ref_stats=None if stats is None else stats[k])
+            # the reference divides unconditionally (ZeroDivisionError on an empty class, :199); keep that behaviour
+            lines[i] = f"Similar images percentage={similar_cnt/total:2.2f}%, positive={similar_cnt}, total={total}"
+            if say is not None:
+                say(lines[i])
+            if progress is not None:
+                progress.update(1)
+        return lines
+
     try:
         import tqdm
-        it = tqdm.tqdm(ref_class_paths)
+        bar = tqdm.tqdm(total=len(ref_class_paths))
     except ImportError:
-        it = ref_class_paths
-    stats = None if args.gallery else all_ref_stats(model, ref_class_paths, args.ref_img_per_class, args.device)
-    for i, ref_class_path in enumerate(it):
-        similar_cnt, total, _ = filter_class(model, ref_class_path, unfiltered_class_paths[i], clean_dir, unclean_dir,
-                                             batch_size=args.batch_size, ref_img_per_class=args.ref_img_per_class,
-                                             gallery=args.gallery, threshold=args.threshold, device=args.device,
-                                             ref_stats=None if stats is None else stats[i])
-        # the reference divides unconditionally (ZeroDivisionError on an empty class, :199); keep that behaviour
-        print(f"Similar images percentage={similar_cnt/total:2.2f}%, positive={similar_cnt}, total={total}")
+        bar = None
+    n_gpus = max(1, min(int(args.ngpus), torch.cuda.device_count() or 1, max(1, len(ref_class_paths))))
+    if n_gpus == 1:
+        run_classes(list(range(len(ref_class_paths))), model, args.device, bar, say=print)
+        lines = {}
+    else:
+        # classes are independent problems: class i goes to GPU i mod n (one worker thread + one model replica per GPU; the
+        # library is re-entrant per device and stream).  Summary lines are printed in class order afterwards.
+        from concurrent.futures import ThreadPoolExecutor
+        replicas = [model_factory(f"cuda:{g}") if model_factory is not None else None for g in range(n_gpus)]
+        if any(r is None for r in replicas):
+            replicas = [MobileFaceNetModel(args.savedmodel_path, args.mobilefacenet_dir, device=f"cuda:{g}",
+                                           allow_random_init=args.allow_random_init) for g in range(n_gpus)]
+        def worker(g):
+            with torch.cuda.device(g):
+                return run_classes(list(range(g, len(ref_class_paths), n_gpus)), replicas[g], f"cuda:{g}", bar)
+        with ThreadPoolExecutor(max_workers=n_gpus) as pool:
+            lines = {}
+            for part in pool.map(worker, range(n_gpus)):
+                lines.update(part)
+    if bar is not None:
+        bar.close()
+    for i in sorted(lines):
+        print(lines[i])
 
 
 if __name__ == "__main__":

@@ -151,3 +151,20 @@ def test_gallery_mode_device_resident_model(tmp_path, ffr_lib, cuda_dev):
     for p, k, s in zip(cands, ko, so):
         if abs(s - 0.6) > 1e-3:
             assert os.path.exists(os.path.join(td, "clean" if k else "unclean", "dave", os.path.basename(p)))
+
+
+def test_main_classes_over_two_gpus(tmp_path, capsys, ffr_lib, cuda_dev):
+    """--ngpus 2: the reference's per-class loop (:161) is the embarrassingly parallel axis -- class i runs on GPU i mod 2
+    with its own model replica; tree and summary lines equal the single-GPU run's."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from face_detection_and_recognition_b200.filter_faces_using_reference import main
+    rng = np.random.default_rng(8)
+    ud, rd = _make_dataset(str(tmp_path), rng, classes=("a", "b", "c", "d", "e"))
+    outs = []
+    for n, td in ((1, str(tmp_path / "o1")), (2, str(tmp_path / "o2"))):
+        main(["--ud", ud, "--rd", rd, "--td", td, "-b", "16", "-r", "8", "--ngpus", str(n)], model_factory=lambda d: TinyEmbedNet(d))
+        text = capsys.readouterr().out
+        outs.append((sorted(l for l in text.splitlines() if l.startswith("Similar images")),
+                     sorted(os.path.relpath(p, td) for p in glob.glob(os.path.join(td, "*", "*", "*.jpg")))))
+    assert outs[0] == outs[1] and len(outs[0][0]) == 5
