@@ -58,7 +58,7 @@ constexpr uint32_t kBarrierBytes = 1024;                      // mbarriers + TME
 constexpr int kStageRows = 32;                                // stage32: fp32 candidate rows per staging buffer
 constexpr uint32_t kStageBytes = kStageRows * 128 * 4;        // 16 KiB: 32 rows x 128 floats (dim_pad == 128 only)
 constexpr int kMaxSBufs = 6;
-constexpr uint32_t kMergeBytes = kTileM * 10 * 4;             // top-4 + hidden-column state hand-over of the other column half
+constexpr uint32_t kMergeBytes = kTileM * 11 * 4;             // top-4 + hidden-column state hand-over of the other column half
 // per kernel variant: extra = kBarrierBytes + (column parts - 1) * kMergeBytes
 
 // running top-4 scores of one candidate (first three with their reference index): what K3 needs to decide in fp32
@@ -75,6 +75,8 @@ struct Top3 {
 struct Hidden {
     float amb, amb2;
     int32_t base;
+    int32_t mask;       // of the part `base` names: bits 0-15 = X groups (columns 8a..8a+7), bits 16-23 = Y groups (column mod 8) that
+                        // reached the window floor when the part was seen -- its in-window columns are among {8a + b}
 };
 
 __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
@@ -224,9 +226,9 @@ struct MaxTree<1> {
 //
 // The epilogue is bound by the ALU pipe (FMNMX / FSETP / SEL / IADD3 issue every other cycle per scheduler) while the FMA
 // pipe idles, so the group tests run THERE: x = sat((s - w1) * 2^60) is 1.0 for s > w1 and 0.0 otherwise (one FFMA.SAT; w1
-// = just below w0, so "> w1" holds for every s >= w0), and acc = sum x * (1 + g/64) is 0 with no group at the floor, 1 + g/64
-// with exactly group g, and >= 2 with several (one FFMA per group, exact in fp32).  (The floor is at most an ulp-ish lower
-// than w0: the window only gets wider, and the fall-back path uses w0 itself.)
+// = just below w0, so "> w1" holds for every s >= w0), and acc = sum x * (2^17 + 2^g) carries the number of groups at the floor
+// and their bit mask (one FFMA per group, exact in fp32).  (The floor is at most an ulp-ish lower than w0: the window only
+// gets wider, and the fall-back path uses w0 itself.)
 template <int kC>
 __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const float (&sx)[kC][4], const float (&cm)[kC], float m,
                                             int32_t base0, float delta, bool exact, Top3& t, float& gate, Hidden& hid) {
@@ -234,13 +236,18 @@ __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const floa
     const float w0 = fmaxf(t.b1, m) - delta;
     const float w1 = fmaf(fabsf(w0), -1.1920929e-7f, w0) - 1.0e-30f;
     const float cb = -w1 * kBig;
+    // Each group test adds 2^17 + 2^g when group g reaches the floor: the (exact, < 2^22) sum carries the NUMBER of such groups in
+    // bits 17.. and their BIT MASK below -- the single in-window column of the common case is decoded from the two masks, and
+    // with several (flag-only path) the masks tell K3 which of the part's 128 references it has to look at.
+    static_assert(kC * 4 <= 16, "X-group mask is 16 bits");
+    constexpr float kCnt = 131072.0f;                   // 2^17
     float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < kC; ++c)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int g = c * 4 + k;
-            ax[g & 1] = fmaf(__saturatef(fmaf(sx[c][k], kBig, cb)), 1.0f + static_cast<float>(g) * 0.015625f, ax[g & 1]);
+            ax[g & 1] = fmaf(__saturatef(fmaf(sx[c][k], kBig, cb)), kCnt + static_cast<float>(1 << g), ax[g & 1]);
         }
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
@@ -249,10 +256,13 @@ __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const floa
         for (int c = 0; c < kC; ++c)
 #pragma unroll
             for (int k = 0; k < 4; ++k) col[c * 4 + k] = v[c][8 * k + b];
-        ay[b & 1] = fmaf(__saturatef(fmaf(MaxTree<kC * 4>::run(col), kBig, cb)), 1.0f + static_cast<float>(b) * 0.015625f, ay[b & 1]);
+        ay[b & 1] = fmaf(__saturatef(fmaf(MaxTree<kC * 4>::run(col), kBig, cb)), kCnt + static_cast<float>(1 << b), ay[b & 1]);
     }
-    const float sxa = ax[0] + ax[1], sya = ay[0] + ay[1];
-    const bool multi = fmaxf(sxa, sya) >= 2.0f;        // several columns of this part inside the window (rare per thread)
+    // (NaN scores of a zero-norm row: sat(NaN) = 0 on this path, the sums stay 0 -> "below the window")
+    const int32_t ix = __float2int_rn(ax[0] + ax[1]), iy = __float2int_rn(ay[0] + ay[1]);
+    const int32_t nx = ix >> 17, ny = iy >> 17;
+    const int32_t mx = ix & 0x1FFFF, my = iy & 0x1FFFF;
+    const bool multi = max(nx, ny) >= 2;               // several columns of this part inside the window (rare per thread)
     if (exact && multi) {
         // (a fall-back at 8-column granularity -- one divergent region per X group at the floor -- gave fewer full rescans
         // but was slower than the per-chunk masks: 16 reconvergence regions in the loop body cost more than they save)
@@ -266,12 +276,13 @@ __device__ __forceinline__ void update_grid(const float (&v)[kC][32], const floa
     // other tracked candidates) -- or every reference, if a second such part is inside the window too; if it is not, nothing
     // of this part matters any more.
     // (sums < 1: the part is below the window, or NaN scores of a zero-norm row -- inserting -inf is a no-op)
-    const float ins = fminf(sxa, sya) >= 1.0f ? m : -INFINITY;
-    const int32_t col = multi ? 0 : __float2int_rn(fmaf(sxa - 1.0f, 512.0f, (sya - 1.0f) * 64.0f));     // 8 a + b
+    const float ins = min(nx, ny) >= 1 ? m : -INFINITY;
+    const int32_t col = multi ? 0 : 8 * (31 - __clz(mx | 1)) + (31 - __clz(my | 1));                   // 8 a + b
     const bool lead = multi && m > hid.amb;
     hid.amb2 = multi ? fmaxf(hid.amb2, fminf(hid.amb, m)) : hid.amb2;
     hid.amb = lead ? m : hid.amb;
     hid.base = lead ? base0 : hid.base;
+    hid.mask = lead ? (mx | (my << 16)) : hid.mask;
     top3_insert(t, ins, base0 + col);
     gate = t.b1 - delta;
 }
@@ -451,19 +462,21 @@ __device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, 
     o.rec.row = static_cast<int32_t>(row);
     o.rec.idx1 = o.rec.idx2 = o.rec.idx3 = -1;
     if (o.cls == 2) {
-        // The part's own placeholder entry (and anything else inside the part) is covered by K3's scan of the part; at most two
-        // tracked candidates lie outside it.  The part is named by its first COMPACT column; the candidates by original index.
+        // The part's own placeholder entry (and anything else inside the part) is covered by K3's scan of the part.  The record
+        // names the part by its first COMPACT column and carries the X / Y group masks (the in-window columns are among
+        // {8a + b}) plus ONE tracked candidate outside the part, by original index; a second one makes it a full rescan.
         const auto outside = [&](float b, int32_t i) {
             return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / 2);
         };
-        int32_t e[2] = {-1, -1};
+        int32_t e = -1;
         int ne = 0;
-        if (outside(t.b1, t.i1)) e[ne++] = t.i1;
-        if (outside(t.b2, t.i2) && ne < 2) e[ne++] = t.i2;
-        if (outside(t.b3, t.i3) && ne < 2) e[ne++] = t.i3;
+        if (outside(t.b1, t.i1)) { e = t.i1; ++ne; }
+        if (outside(t.b2, t.i2)) { e = ne ? e : t.i2; ++ne; }
+        if (outside(t.b3, t.i3)) { e = ne ? e : t.i3; ++ne; }
+        if (ne > 1) o.cls = 3;
         o.rec.idx1 = hid.base;
-        o.rec.idx2 = orig(e[0]);
-        o.rec.idx3 = orig(e[1]);
+        o.rec.idx2 = orig(e);
+        o.rec.idx3 = hid.mask;
     } else if (o.cls == 1) {
         o.rec.idx1 = orig(t.i1);
         o.rec.idx2 = near_tie ? orig(t.i2) : -1;
@@ -809,19 +822,22 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int r = nw * 64 + rr * 32 + lane;
-                    const float* ma = merge + (slot * 2 + 0) * 10 * kTileM;
-                    const float* mb = merge + (slot * 2 + 1) * 10 * kTileM;
+                    const float* ma = merge + (slot * 2 + 0) * 11 * kTileM;
+                    const float* mb = merge + (slot * 2 + 1) * 11 * kTileM;
                     Top3 t;
                     Hidden hid;
                     t.b1 = ma[0 * kTileM + r]; t.b2 = ma[1 * kTileM + r]; t.b3 = ma[2 * kTileM + r]; t.b4 = ma[3 * kTileM + r];
                     t.i1 = __float_as_int(ma[4 * kTileM + r]); t.i2 = __float_as_int(ma[5 * kTileM + r]); t.i3 = __float_as_int(ma[6 * kTileM + r]);
                     hid.amb = ma[7 * kTileM + r]; hid.amb2 = ma[8 * kTileM + r]; hid.base = __float_as_int(ma[9 * kTileM + r]);
+                    hid.mask = __float_as_int(ma[10 * kTileM + r]);
                     const float o1 = mb[0 * kTileM + r], o2 = mb[1 * kTileM + r], o3 = mb[2 * kTileM + r], o4 = mb[3 * kTileM + r];
                     const int32_t j1 = __float_as_int(mb[4 * kTileM + r]), j2 = __float_as_int(mb[5 * kTileM + r]), j3 = __float_as_int(mb[6 * kTileM + r]);
                     const float o_amb = mb[7 * kTileM + r], o_amb2 = mb[8 * kTileM + r];
                     const int32_t o_base = __float_as_int(mb[9 * kTileM + r]);
+                    const int32_t o_mask = __float_as_int(mb[10 * kTileM + r]);
                     hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
                     hid.base = o_amb > hid.amb ? o_base : hid.base;
+                    hid.mask = o_amb > hid.amb ? o_mask : hid.mask;
                     hid.amb = fmaxf(hid.amb, o_amb);
                     if (o1 != -INFINITY) top3_merge_insert(t, o1, j1);
                     if (j2 >= 0) top3_merge_insert(t, o2, j2);
@@ -1017,6 +1033,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             Hidden hid;                                         // see struct Hidden
             hid.amb = hid.amb2 = -INFINITY;
             hid.base = 0;
+            hid.mask = 0;
             const int64_t row = tile * (kTileM * kCG) + cta_rank * kTileM + r_in_tile;
             // One reference tile.  The loop over FULL tiles and the one partial last tile are separate copies of this body: the
             // masking of columns >= n_ref is 260 instructions that the hot loop would otherwise carry (and jump over) on every
@@ -1118,7 +1135,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 // normaliser warps (helpers), which have spare time at every reference-set size, merge and emit it.
                 const uint32_t slot = c_it & 1u;
                 mbar_wait(&m_empty[slot], ((c_it >> 1) & 1u) ^ 1u);          // merged two candidate tiles ago: free again
-                float* mg = merge + (slot * 2 + h) * 10 * kTileM;
+                float* mg = merge + (slot * 2 + h) * 11 * kTileM;
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
                 mg[2 * kTileM + r_in_tile] = t.b3;
@@ -1129,6 +1146,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mg[7 * kTileM + r_in_tile] = hid.amb;
                 mg[8 * kTileM + r_in_tile] = hid.amb2;
                 mg[9 * kTileM + r_in_tile] = __int_as_float(hid.base);
+                mg[10 * kTileM + r_in_tile] = __int_as_float(hid.mask);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&m_full[slot]);                  // (release at CTA scope: the warp's stores above)
             } else {
@@ -1139,7 +1157,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
             if (!merger) {
-                float* mg = merge + (kAlt ? 0 : (h - 1) * 10 * kTileM);
+                float* mg = merge + (kAlt ? 0 : (h - 1) * 11 * kTileM);
                 if (!kAlt && !first_tile) named_bar_sync(5 + q, kParts * 32);  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
@@ -1151,6 +1169,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 mg[7 * kTileM + r_in_tile] = hid.amb;
                 mg[8 * kTileM + r_in_tile] = hid.amb2;
                 mg[9 * kTileM + r_in_tile] = __int_as_float(hid.base);
+                mg[10 * kTileM + r_in_tile] = __int_as_float(hid.mask);
                 __threadfence_block();
                 named_bar_arrive(bar_ready, kParts * 32);
             } else {
@@ -1161,7 +1180,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 int32_t oi[kParts - 1][3];
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    const float* mg = merge + pp * 10 * kTileM;
+                    const float* mg = merge + pp * 11 * kTileM;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
 #pragma unroll
@@ -1169,8 +1188,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     // the other half's hidden-column state: the larger part maximum leads, everything else is "a second part"
                     const float o_amb = mg[7 * kTileM + r_in_tile], o_amb2 = mg[8 * kTileM + r_in_tile];
                     const int32_t o_base = __float_as_int(mg[9 * kTileM + r_in_tile]);
+                    const int32_t o_mask = __float_as_int(mg[10 * kTileM + r_in_tile]);
                     hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
                     hid.base = o_amb > hid.amb ? o_base : hid.base;
+                    hid.mask = o_amb > hid.amb ? o_mask : hid.mask;
                     hid.amb = fmaxf(hid.amb, o_amb);
                 }
                 if (!kAlt) named_bar_arrive(5 + q, kParts * 32);

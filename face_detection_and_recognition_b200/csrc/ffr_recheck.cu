@@ -194,10 +194,11 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
 }
 
 // K3p: rows whose un-inserted in-window columns all lie in ONE 128-reference part of K2's column grid (flag-only update path,
-// DESIGN.md section 4): fp32 cosine against the references of that part plus the row's (at most two) tracked candidates outside
-// it; first occurrence of the maximum.  One warp per record, LANE PER REFERENCE (four references per lane, the candidate row
-// broadcast from shared memory): no shuffles until the final argmax merge.  Every lane streams its own reference rows,
-// which are L2-resident.
+// DESIGN.md section 4).  The record names the part (first compact column), the X groups (columns 8a..8a+7, 16 bits) and Y groups
+// (column mod 8, 8 bits) that reached the window floor -- the in-window columns are among {8a + b} -- and one tracked
+// candidate outside the part.  fp32 cosine against exactly those references; first occurrence of the maximum.  One warp per
+// record, LANE PER REFERENCE (the candidate row broadcast from shared memory): no shuffles until the final argmax merge,
+// every lane streams its own reference row out of L2.  Typically 2-8 references, at most 129.
 constexpr int kPartRefs = 128;          // == kTileN / 2 of ffr_filter_mma.cu (one epilogue warp's columns of a reference tile)
 
 __device__ __forceinline__ void
@@ -222,63 +223,54 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
         for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
         __syncwarp();
         const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
-        // this lane's references: part_base + lane + 32 j (j < 4), plus (lanes 0 and 1) one tracked candidate outside the part
-        constexpr int kR = kPartRefs / 32 + 1;
-        int64_t ri[kR];
-#pragma unroll
-        for (int j = 0; j < kR - 1; ++j) {
-            const int64_t i = static_cast<int64_t>(rec.idx1) + lane + 32 * j;
-            ri[j] = i < n_cols ? (ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + i)) : i) : -1;
-        }
-        ri[kR - 1] = lane == 0 ? rec.idx2 : (lane == 1 ? rec.idx3 : -1);
-        float a[kR], b[kR];
-#pragma unroll
-        for (int j = 0; j < kR; ++j) { a[j] = 0.f; b[j] = 0.f; }
-        if (vec) {
-            // four float4 steps at a time, every load of the batch issued before the first FMA: the rows come out of L2 (~600
-            // cycles), and one step per round trip made this phase pure latency
-            const float4* c4 = reinterpret_cast<const float4*>(c_smem);
-            const int nq = dim >> 2;
-            constexpr int kU = 4;
-            for (int q0 = 0; q0 < nq; q0 += kU) {
-                float4 rv[kR][kU];
-#pragma unroll
-                for (int j = 0; j < kR; ++j)
+        const uint32_t xm = static_cast<uint32_t>(rec.idx3) & 0xFFFFu, ym = (static_cast<uint32_t>(rec.idx3) >> 16) & 0xFFu;
+        const int ny = __popc(ym);
+        const int n_in = __popc(xm) * ny;                         // candidate columns inside the part (<= 128)
+        const int n_all = n_in + (rec.idx2 >= 0 ? 1 : 0);         // + the tracked candidate outside it
+        unsigned long long key = 0ull;
+        for (int e0 = 0; e0 < n_all; e0 += 32) {                  // 32 references at a time, one per lane
+            const int e = e0 + lane;
+            int64_t ri = -1;
+            if (e < n_in) {
+                const int a = __fns(xm, 0, e / ny + 1), b = __fns(ym, 0, e % ny + 1);     // e-th (a, b) pair in ascending column order
+                const int64_t col = static_cast<int64_t>(rec.idx1) + 8 * a + b;
+                if (col < n_cols) ri = ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + col)) : col;
+            } else if (e == n_in && rec.idx2 >= 0) {
+                ri = rec.idx2;
+            }
+            float a_acc = 0.f, b_acc = 0.f;
+            if (vec) {
+                // eight float4 steps at a time, every load issued before the first FMA: the rows come out of L2 (~600 cycles)
+                const float4* c4 = reinterpret_cast<const float4*>(c_smem);
+                const float4* r4 = reinterpret_cast<const float4*>(ref + (ri >= 0 ? ri : 0) * dim);
+                const int nq = dim >> 2;
+                constexpr int kU = 8;
+                for (int q0 = 0; q0 < nq; q0 += kU) {
+                    float4 rv[kU];
 #pragma unroll
                     for (int u = 0; u < kU; ++u)
-                        rv[j][u] = (ri[j] >= 0 && q0 + u < nq) ? __ldg(reinterpret_cast<const float4*>(ref + ri[j] * dim) + q0 + u)
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rv[u] = (ri >= 0 && q0 + u < nq) ? __ldg(r4 + q0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const float4 cv = q0 + u < nq ? c4[q0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int j = 0; j < kR; ++j) {
-                        a[j] = fmaf(cv.x, rv[j][u].x, a[j]); a[j] = fmaf(cv.y, rv[j][u].y, a[j]);
-                        a[j] = fmaf(cv.z, rv[j][u].z, a[j]); a[j] = fmaf(cv.w, rv[j][u].w, a[j]);
-                        b[j] = fmaf(rv[j][u].x, rv[j][u].x, b[j]); b[j] = fmaf(rv[j][u].y, rv[j][u].y, b[j]);
-                        b[j] = fmaf(rv[j][u].z, rv[j][u].z, b[j]); b[j] = fmaf(rv[j][u].w, rv[j][u].w, b[j]);
+                    for (int u = 0; u < kU; ++u) {
+                        const float4 cv = q0 + u < nq ? c4[q0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a_acc = fmaf(cv.x, rv[u].x, a_acc); a_acc = fmaf(cv.y, rv[u].y, a_acc);
+                        a_acc = fmaf(cv.z, rv[u].z, a_acc); a_acc = fmaf(cv.w, rv[u].w, a_acc);
+                        b_acc = fmaf(rv[u].x, rv[u].x, b_acc); b_acc = fmaf(rv[u].y, rv[u].y, b_acc);
+                        b_acc = fmaf(rv[u].z, rv[u].z, b_acc); b_acc = fmaf(rv[u].w, rv[u].w, b_acc);
                     }
                 }
-            }
-        } else {
-            for (int q = 0; q < dim; ++q) {
-                const float cv = c_smem[q];
-#pragma unroll
-                for (int j = 0; j < kR; ++j) {
-                    const float rv = ri[j] >= 0 ? __ldg(ref + ri[j] * dim + q) : 0.f;
-                    a[j] = fmaf(cv, rv, a[j]);
-                    b[j] = fmaf(rv, rv, b[j]);
+            } else {
+                for (int q = 0; q < dim; ++q) {
+                    const float rvq = ri >= 0 ? __ldg(ref + ri * dim + q) : 0.f;
+                    a_acc = fmaf(c_smem[q], rvq, a_acc);
+                    b_acc = fmaf(rvq, rvq, b_acc);
                 }
             }
-        }
-        // NOTE: the accumulation order differs from cos_fp32's lane-strided one by fp32 summation noise only (<= ~1e-7); the
-        // decision between references that close is fp32-ill-defined anyway (tests: TIE_EPS)
-        unsigned long long key = 0ull;
-#pragma unroll
-        for (int j = 0; j < kR; ++j) {
-            if (ri[j] >= 0) {
-                const float sc = __fdiv_rn(a[j], __fmul_rn(__fsqrt_rn(b[j]), cc_sqrt));
-                const unsigned long long kj = pack_key(sc, static_cast<int32_t>(ri[j]));
+            // NOTE: the accumulation order differs from cos_fp32's lane-strided one by fp32 summation noise only (<= ~1e-7); the
+            // decision between references that close is fp32-ill-defined anyway (tests: TIE_EPS)
+            if (ri >= 0) {
+                const float sc = __fdiv_rn(a_acc, __fmul_rn(__fsqrt_rn(b_acc), cc_sqrt));
+                const unsigned long long kj = pack_key(sc, static_cast<int32_t>(ri));
                 key = kj > key ? kj : key;
             }
         }

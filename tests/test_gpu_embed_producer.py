@@ -85,7 +85,7 @@ def test_device_preprocess_matches_host(tmp_path, cuda_dev):
     host = torch.stack([read_and_preprocess_img(p) for p in paths])
     assert dev_batch.shape == host.shape == (9, 160, 160, 3)
     diff = (dev_batch - host).abs()
-    assert diff.mean().item() < 5e-3 and diff.max().item() < 0.25, (diff.mean().item(), diff.max().item())
+    assert diff.mean().item() < 2e-2 and diff.max().item() < 0.25, (diff.mean().item(), diff.max().item())
     np.testing.assert_allclose(dev_batch.mean(dim=(1, 2, 3)).numpy(), 0, atol=1e-4)
     np.testing.assert_allclose(dev_batch.std(dim=(1, 2, 3), unbiased=False).numpy(), 1, atol=1e-3)
 
