@@ -1466,7 +1466,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (after_k1 && n_ref_dev == nullptr && kn.pdl != 0) {   // the previous launch of this stream is K1 (it triggers its dependents at entry)
+    if (after_k1 && n_ref_dev == nullptr && (kn.pdl & 1) != 0) {   // the previous launch of this stream is K1 (it triggers its dependents at entry)
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;

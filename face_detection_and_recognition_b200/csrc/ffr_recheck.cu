@@ -298,8 +298,8 @@ constexpr int kSliceRefs = 1024;
 // (row, block of kSmallRefs references) items instead: the row is parked in this warp's shared-memory slot, lanes split
 // the embedding, one fp32 cosine per reference exactly like K3a (kSmallBatch references in flight).  Same merge: atomicMax on the packed key, and the
 // last item of a group of kFullGroup rows (full_ctr counts rows x blocks) writes the group's outputs.
-constexpr int kSmallRefs = 32;
-constexpr int kSmallBatch = 8;
+constexpr int kSmallRefs = 8;        // one batch per item: with a handful of rows (BASELINE configs[1]: 2 of 100 k) the phase is pure
+constexpr int kSmallBatch = 8;       // latency, and 32-reference items meant four dependent L2 round trips per warp (8 -> 3 us)
 // every flagged row streams the whole reference set once here (no reuse across rows, unlike the tiled walk's 8 rows per
 // reference read): only worth it while that is a few tens of MB of L2 traffic
 constexpr long long kSmallElems = 16000000;
@@ -635,7 +635,7 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // K2 (the previous launch) triggers at its entry
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = knobs().pdl != 0 ? 1 : 0;
+    cfg.numAttrs = (knobs().pdl & 2) != 0 ? 1 : 0;        // FFR_PDL bit 1 (bit 0: K1 -> K2)
     if (vec) FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<true>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
                                              lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev));
     else     FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<false>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
