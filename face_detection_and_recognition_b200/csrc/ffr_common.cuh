@@ -95,6 +95,39 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// |c - m|_2 of one row with EXACTLY the per-lane element assignment, accumulation order and reduction tree the streaming
+// filter K2s uses for an Euclid score (ffr_filter_fp32.cu), so that K5's threshold -- the largest reference-to-mean distance --
+// is bit-identical to the distance the filter later computes for that same reference as a candidate (the reference gets both
+// from one np.linalg.norm: the farthest reference always passes `<= thres`, filter_faces_using_reference.py:88-99,189).
+// mode (k2s_dist_mode on the host): 0 = scalar lane-strided; 1, 2, 4, 8 = float4 #(lane + 32 j), j < mode; 16 / 32 = sub-warp
+// form, 8 / 16 lanes per row with float4 #(sub + L j), j < 4.  The whole warp calls it; every lane returns the distance.
+__device__ __forceinline__ float k2s_euclid_dist(const float* __restrict__ c, const float* m, int32_t dim, int lane, int mode) {
+    float a = 0.f;
+    if (mode == 0) {
+        for (int k = lane; k < dim; k += 32) { const float d = c[k] - m[k]; a = fmaf(d, d, a); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    } else {
+        const float4* c4 = reinterpret_cast<const float4*>(c);
+        const float4* m4 = reinterpret_cast<const float4*>(m);
+        const int nvec = dim >> 2;
+        const int L = mode >= 16 ? mode / 2 : 32, nj = mode >= 16 ? 4 : mode, sub = lane % L;
+        for (int j = 0; j < nj; ++j) {
+            const int k = sub + L * j;
+            if (k < nvec) {
+                const float4 cv = c4[k], mv = m4[k];
+                float d;
+                d = cv.x - mv.x; a = fmaf(d, d, a);
+                d = cv.y - mv.y; a = fmaf(d, d, a);
+                d = cv.z - mv.z; a = fmaf(d, d, a);
+                d = cv.w - mv.w; a = fmaf(d, d, a);
+            }
+        }
+        for (int o = L / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    return __fsqrt_rn(a);
+}
+
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -315,6 +348,7 @@ int launch_first_match_stream(float* g_feat, float* g_bbox, int32_t* g_count, in
                               float harsh_thres, int32_t* match_idx, cudaStream_t s);
 void set_mma_prof_buffer(unsigned long long* dev_ptr);   // diagnostics: [grid][16] stall-cycle counters of K2
 int launch_ref_stats(const float* ref_feat, int32_t n_ref, int32_t dim, float* mean, float* thres, cudaStream_t s);
+int k2s_dist_mode(const float* rows, int32_t dim);       // which K2s form scores (n_ref = 1, Euclid) rows of this width / alignment
 int launch_pack_results(const uint8_t* keep, const int32_t* idx, int64_t m, int64_t m_pad, uint8_t* packed,
                         cudaStream_t s);
 int launch_unpack_results(const uint8_t* packed, int64_t m, int64_t m_pad, int nranks, uint8_t* keep, int32_t* idx,

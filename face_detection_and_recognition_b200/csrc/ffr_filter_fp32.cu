@@ -298,8 +298,8 @@ filter_fp32_generic_kernel(const float* __restrict__ ref, int64_t n_ref, const f
 //   mean[d] = (sum_i x[i,d]) / n   (np.mean over axis 0: sequential fp32 accumulation for n <= 8 rows per
 //   pairwise block is not reproduced bit-for-bit; tolerance documented in the tests)
 __global__ void __launch_bounds__(256)
-ref_stats_kernel(const float* __restrict__ x, int32_t n, int32_t dim, float* __restrict__ mean, float* __restrict__ thres) {
-    extern __shared__ float s_mean[];                 // dim floats + 8 warp maxima
+ref_stats_kernel(const float* __restrict__ x, int32_t n, int32_t dim, float* __restrict__ mean, float* __restrict__ thres, int mode) {
+    extern __shared__ __align__(16) float s_mean[];   // dim floats + 8 warp maxima
     float* s_max = s_mean + dim;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) {
         float acc = 0.f;
@@ -311,12 +311,8 @@ ref_stats_kernel(const float* __restrict__ x, int32_t n, int32_t dim, float* __r
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float wmax = 0.f;
-    for (int i = warp; i < n; i += nw) {
-        float a = 0.f;
-        for (int d = lane; d < dim; d += 32) { const float t = s_mean[d] - x[static_cast<int64_t>(i) * dim + d]; a = fmaf(t, t, a); }
-        a = warp_sum(a);
-        wmax = fmaxf(wmax, __fsqrt_rn(a));
-    }
+    for (int i = warp; i < n; i += nw)                // the distance K2s will compute for this row as a candidate, bit for bit
+        wmax = fmaxf(wmax, k2s_euclid_dist(x + static_cast<int64_t>(i) * dim, s_mean, dim, lane, mode));
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -391,9 +387,18 @@ int launch_filter_fp32(const float* ref, int64_t n_ref, const float* cand, int64
 #undef FFR_DISPATCH
 }
 
+// mirrors launch_filter_fp32's choice of kernel for (n_ref = 1, metric Euclid)
+int k2s_dist_mode(const float* rows, int32_t dim) {
+    const bool vec_ok = (dim % 4 == 0) && dim <= 1024 && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
+    if (!vec_ok) return 0;
+    if ((dim == 128 || dim == 256) && knobs().k2s_subwarp != 0) return dim == 128 ? 16 : 32;
+    const int nv = (dim + 127) / 128;
+    return nv <= 1 ? 1 : (nv <= 2 ? 2 : (nv <= 4 ? 4 : 8));
+}
+
 int launch_ref_stats(const float* ref_feat, int32_t n_ref, int32_t dim, float* mean, float* thres, cudaStream_t s) {
     const size_t smem = (static_cast<size_t>(dim) + 8) * sizeof(float);
-    ref_stats_kernel<<<1, 256, smem, s>>>(ref_feat, n_ref, dim, mean, thres);
+    ref_stats_kernel<<<1, 256, smem, s>>>(ref_feat, n_ref, dim, mean, thres, k2s_dist_mode(ref_feat, dim));
     FFR_LAUNCH_CHECK("ref_stats");
     return FFR_OK;
 }

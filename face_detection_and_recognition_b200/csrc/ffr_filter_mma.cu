@@ -24,14 +24,18 @@
 //     phases carried incrementally.  warps 2-9: epilogue, one thread per (candidate row, column half): the
 //     max/argmax over references is a pure in-register reduction over TMEM columns -- no shuffles; the two column
 //     halves of a row are merged through shared memory once per candidate tile.  kNorm: warps 10-11 L2-normalise
-//     the fp32 rows of the CTA's next candidate tile into the fp16 workspace (K1 inside K2).
+//     the fp32 rows of the CTA's next candidate tile (K1 inside K2) -- into the fp16 workspace, or (stage32, 128-d rows)
+//     from TMA-staged fp32 rows straight into the swizzled A stage; in stage32 they also run the end-of-tile work
+//     (merge of the column halves, classification, K3's lists) for the epilogue warps.
 //   * the accumulator is double buffered in TMEM (2 x 256 of the 512 columns): the MMAs of reference tile
 //     t+1 overlap the epilogue of tile t.
 //   * epilogue per reference tile: four tcgen05.ld in flight -> stage released -> four 3-input-max trees -> the update
-//     path update_grid (X/Y group maxima locate the single in-window column; group tests on the FMA pipe), unconditional
-//     for short reference sets, behind one branch on the tile maximum for long ones.  Ascending column order + strict
-//     '>' = np.argmax first occurrence.  The running top-4 (+ the "hidden column" level amb) is what K3 needs to make
-//     the index and keep bit exact in fp32.
+//     path update_grid (X/Y group maxima locate the single in-window column; group tests on the FMA pipe deliver the
+//     groups' count and bit masks), unconditional for short reference sets, behind one branch on the tile maximum for
+//     long ones.  Ascending column order + strict '>' = np.argmax first occurrence.  The running top-4 (+ the "hidden
+//     column" state: the part with several in-window columns and its X/Y masks) is what K3 needs to make the index and
+//     keep bit exact in fp32.  Duplicate reference rows may have been folded before (ffr_dedup.cu): columns then map back
+//     to original indices through ref_map in the tail.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -302,16 +306,9 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's CTA 0
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // arrive on CTA 0's copy of the barrier
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(smem_u32(bar)) : "memory");
-}
-// Same, without release semantics: for "this warp has finished READING the accumulator stage" (t_empty).  The reads
-// are complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; no generic-proxy writes need to
-// become visible.  The .release.cluster form compiles to MEMBAR.ALL.GPU + arrive, ~1 us per reference tile.
+// Arrive on CTA 0's copy of a barrier WITHOUT release semantics: for "this warp has finished READING the accumulator stage"
+// (t_empty).  The reads are complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; no generic-proxy
+// writes need to become visible.  The .release.cluster form compiles to MEMBAR.ALL.GPU + arrive, ~1 us per reference tile.
 __device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"

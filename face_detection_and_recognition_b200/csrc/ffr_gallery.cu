@@ -18,8 +18,8 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 ref_stats_batched_kernel(const float* __restrict__ x, const int32_t* __restrict__ offsets, int32_t dim,
-                         float* __restrict__ mean, float* __restrict__ thres) {
-    extern __shared__ float s_mean[];                 // dim floats + 8 warp maxima
+                         float* __restrict__ mean, float* __restrict__ thres, int mode) {
+    extern __shared__ __align__(16) float s_mean[];   // dim floats + 8 warp maxima
     float* s_max = s_mean + dim;
     const int c = blockIdx.x;
     const int32_t lo = offsets[c], hi = offsets[c + 1];
@@ -34,12 +34,8 @@ ref_stats_batched_kernel(const float* __restrict__ x, const int32_t* __restrict_
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float wmax = 0.f;
-    for (int i = lo + warp; i < hi; i += nw) {
-        float a = 0.f;
-        for (int d = lane; d < dim; d += 32) { const float t = s_mean[d] - x[static_cast<int64_t>(i) * dim + d]; a = fmaf(t, t, a); }
-        a = warp_sum(a);
-        wmax = fmaxf(wmax, __fsqrt_rn(a));
-    }
+    for (int i = lo + warp; i < hi; i += nw)          // the distance K2s will compute for this row as a candidate, bit for bit
+        wmax = fmaxf(wmax, k2s_euclid_dist(x + static_cast<int64_t>(i) * dim, s_mean, dim, lane, mode));
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -138,7 +134,8 @@ int launch_ref_stats_batched(const float* ref_feat, const int32_t* offsets, int3
                              float* thres, cudaStream_t s) {
     if (n_classes == 0) return FFR_OK;
     const size_t smem = (static_cast<size_t>(dim) + 8) * sizeof(float);
-    ref_stats_batched_kernel<<<static_cast<unsigned>(n_classes), 256, smem, s>>>(ref_feat, offsets, dim, mean, thres);
+    ref_stats_batched_kernel<<<static_cast<unsigned>(n_classes), 256, smem, s>>>(ref_feat, offsets, dim, mean, thres,
+                                                                                    k2s_dist_mode(ref_feat, dim));
     FFR_LAUNCH_CHECK("ref_stats_batched");
     return FFR_OK;
 }

@@ -73,3 +73,17 @@ def test_first_match_capacity_and_no_bbox(ops):
     assert found[0] and faceid[0] == 3
     with pytest.raises(RuntimeError):
         gal.match(x[5])
+
+
+@pytest.mark.parametrize("dim,n", [(128, 32), (256, 17), (512, 32), (100, 9), (1024, 5), (130, 12), (384, 40)])
+def test_farthest_reference_passes_its_own_threshold(ops, dim, n):
+    """The reference takes the threshold (:88-99) and the keep test (:189) from the same np.linalg.norm, so the reference
+    image that DEFINES the threshold always passes `<= thres` when it is also a candidate.  K5 computes its distances with
+    the arithmetic of the streaming filter (same per-lane element order, same reduction tree): bit-identical, no 1-ulp flip."""
+    rng = np.random.default_rng(dim + n)
+    for trial in range(20):
+        x = torch.from_numpy((rng.standard_normal((n, dim)) * rng.uniform(0.5, 12)).astype(np.float32)).cuda()
+        for mean, thres in (ops.ref_mean_and_thres(x), tuple(t[0:1] if t.dim() == 2 else t[0] for t in ops.ref_mean_and_thres_batched(x, [n]))):
+            res = ops.face_filter(mean.reshape(1, -1), x, float(thres), metric="euclid")
+            assert bool(res.keep.all()), (trial, float(thres), float(res.best_val.max()))
+            assert float(res.best_val.max()) == float(thres)
