@@ -55,6 +55,10 @@ WORKLOADS = {
     # candidate has >= 5 leaders that only fp32 can tell apart -- K3's part rescan decides all of them
     "near8": dict(n_ref=10_000, n_cand=1_250_000, dim=512, adv_every=1250, n_dup=0, dup_group=8, sib_cos=0.99995,
                   name="near-identical gallery: 1250 identities x 8 enrolments (4 exact copies + 4 at cos 0.99995) x 1.25M cand x 512-d"),
+    # configs[1]'s label says "HBM-bound regime", which holds for N <~ 530 references only (add an N <= 256 sub-case that
+    # truly is): 256 references, ONE reference tile per candidate tile -- K2 has to stream the fp32 candidates at HBM speed
+    "hbm256": dict(n_ref=256, n_cand=2_000_000, dim=128, adv_every=2000, n_dup=2, bound="hbm",
+                   name="HBM-bound sub-case of configs[1]: 256 ref x 2M cand x 128-d, threshold filter"),
     # the reference's literal mode (filter_faces_using_reference.py:186-189) at scale: ONE mean vector, Euclid keep test.
     # 0.5 FLOP/byte: the HBM-bound end of the path (exact fp32 streaming kernel K2s, no tensor cores)
     "n1": dict(n_ref=1, n_cand=10_000_000, dim=128, metric="euclid", thr=1.2, adv_every=0, n_dup=0,
@@ -472,6 +476,12 @@ def roofline_of(r, pk, traffic):
     # FLOPs of the contraction K2 actually ran: bit-identical reference rows are folded before the scan (ffr_dedup.cu)
     n_scanned = int(r["stats"].get("refs_scanned") or n_ref)
     flops = 2.0 * n_scanned * n_cand * dim
+    if w.get("bound") == "hbm":            # tensor-core kernel, but the candidates' fp32 rows are what takes the time
+        gbs = hbm_bytes / (r["k2_ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "filter_mma_kernel (K2, stage32)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": gbs / pk["hbm"], "frac_whole_step": hbm_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["source"],
+                "k2_ms": r["k2_ms"], "k2_share_of_step": r["k2_ms"] / ms_step, "bytes_per_launch": hbm_bytes,
+                "tflops": flops / (r["k2_ms"] * 1e-3) / 1e12, "traffic": traffic}
     ach = flops / (r["k2_ms"] * 1e-3) / 1e12
     ach_step = flops / (ms_step * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "filter_mma_kernel (K2)", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",

@@ -87,7 +87,7 @@ const Knobs* read_knobs() {
     k->k1_rows = env_int("FFR_K1_ROWS", 8);
     k->k2s_subwarp = env_int("FFR_K2S_SUBWARP", 1);
     k->dedup_refs = env_int("FFR_DEDUP_REFS", 1);
-    k->small_n = env_int("FFR_SMALL_N", 1);
+    k->tail_offload = env_int("FFR_TAIL_OFFLOAD", -1);
     k->pdl = env_int("FFR_PDL", 1);
     return k;
 }

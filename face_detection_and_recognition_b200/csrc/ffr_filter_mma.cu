@@ -542,7 +542,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
     // kInstr: the instrumented build (in-kernel cycle counters, score dump, epilogue diagnostics).  The production
     // instantiation contains none of it: the counters alone were half a dozen spilled 64-bit values per role.
     constexpr bool kNorm = kNormMode != 0;
-    constexpr bool st32 = kNormMode == 2;
+    constexpr bool st32 = kNormMode >= 2;
+    // stage32 comes in two forms: kNormMode 2 hands the end-of-tile work (merge of the column halves, classification, K3's
+    // lists) to the two normaliser warps -- right when the epilogue paces the kernel (>= 2 reference tiles per candidate tile);
+    // kNormMode 3 keeps it in the epilogue warps -- right when there is ONE reference tile per candidate tile (<= 256
+    // references: the HBM-bound regime), where the normaliser warps are the busy ones and the epilogue has cycles to spare.
+    constexpr bool kOffload = kNormMode == 2;
     constexpr int kEW = 8;                                          // epilogue warps
     constexpr int kAccN = kTileN;                                   // references per accumulator stage
     const unsigned long long* const prof_on = kInstr ? p.prof : nullptr;
@@ -911,11 +916,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
                 // the A tile of candidate tile n_done is on its way to the tensor core; candidate tile n_done - 2 finished its
                 // epilogue a whole tile ago: merge + emit it now, while the MMAs of tile n_done - 1 run
-                if (n_done >= 2u) merge_tile(n_done - 2u);
+                if (kOffload && n_done >= 2u) merge_tile(n_done - 2u);
                 ++n_done;
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
-            for (uint32_t u = n_done >= 2u ? n_done - 2u : 0u; u < n_done; ++u) merge_tile(u);     // drain: the last two tiles
+            if (kOffload)
+                for (uint32_t u = n_done >= 2u ? n_done - 2u : 0u; u < n_done; ++u) merge_tile(u);   // drain: the last two tiles
             if (pr && lane == 0) {
                 p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
                 p.prof[blockIdx.x * 32 + 14] = n_done;
@@ -1124,8 +1130,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // warps of ONE lane quadrant (ids 1+q / 5+q, alternating with the tile parity so that an early arrive for tile
             // n + 2 cannot complete tile n's barrier); with CTA-wide barriers every quadrant waited for the slowest warp.
             const long long t_tail0 = pr ? clock64() : 0;
-            if constexpr (st32) {
-                // stage32: the tail is NOT run here.  Merging the two column halves, classifying the row and appending to K3's
+            if constexpr (kOffload) {
+                // stage32 with several reference tiles per candidate tile: the tail is NOT run here.  Merging the two column halves, classifying the row and appending to K3's
                 // lists is ~300 dependent instructions that used to stall this warp for as long as a reference tile's hot loop
                 // (with four reference tiles per candidate tile -- BASELINE configs[1] -- a fifth of the epilogue's time).  Both
                 // halves park their state in one of two shared-memory slots and go on with the next candidate tile; the two
@@ -1358,8 +1364,10 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     // stage32 (fused normalisation, 128-d rows): fp32 rows staged by TMA, two A stages (the normaliser fills one while the
     // MMAs read the other), the B ring gets what is left (>= 2 stages); the tail's hand-over buffer is two slots x two halves
     const bool st32 = fuse && filter_mma_stage32_ok(dim, dim_pad);
-    const uint32_t extra = kBarrierBytes + (st32 ? 4 : 1) * kMergeBytes;
-    int s_bufs = st32 ? kMaxSBufs - 1 : 0;                 // five 16 KB staging buffers leave three B stages beside the merge slots
+    // (FFR_TAIL_OFFLOAD: -1 auto = offload from two reference tiles per candidate tile up, 0 / 1 force)
+    const bool offload = st32 && (kn.tail_offload >= 0 ? kn.tail_offload != 0 : n_ref > kTileN);
+    const uint32_t extra = kBarrierBytes + (offload ? 4 : 1) * kMergeBytes;
+    int s_bufs = st32 ? (offload ? kMaxSBufs - 1 : kMaxSBufs) : 0;   // (with the merge slots: five 16 KB staging buffers leave three B stages)
     if (st32) {
         a_stages = 2;
         while (s_bufs > 3 && kSmemLimit - extra - s_bufs * kStageBytes < a_stages * a_stage + 2 * b_stage) --s_bufs;
@@ -1419,13 +1427,13 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     // fall-back code in the hot loop); the instrumented build (tools/diag_mma.py, the tests' score dump) and the
     // cta_group::1 fall-back (odd SM counts, FFR_CTA_GROUP=1) read them at run time.
     const bool instr = prof != nullptr || dbg_scores != nullptr || p.epi_mode != 0;
-    const int nm = st32 ? 2 : (fuse ? 1 : 0);
+    const int nm = st32 ? (offload ? 2 : 3) : (fuse ? 1 : 0);
 #define FFR_K(CG, NM, E, A, I) filter_mma_kernel<CG, NM, E, A, I>
 #define FFR_K_POLICY(NM) {FFR_K(2, NM, 0, 0, false), FFR_K(2, NM, 0, 1, false), FFR_K(2, NM, 1, 0, false), FFR_K(2, NM, 1, 1, false)}
-    static const KernelFn prod2[3][4] = {FFR_K_POLICY(0), FFR_K_POLICY(1), FFR_K_POLICY(2)};
-    static const KernelFn instr2[3] = {FFR_K(2, 0, 2, 2, true), FFR_K(2, 1, 2, 2, true), FFR_K(2, 2, 2, 2, true)};
-    static const KernelFn prod1[3] = {FFR_K(1, 0, 2, 2, false), FFR_K(1, 1, 2, 2, false), FFR_K(1, 2, 2, 2, false)};
-    static const KernelFn instr1[3] = {FFR_K(1, 0, 2, 2, true), FFR_K(1, 1, 2, 2, true), FFR_K(1, 2, 2, 2, true)};
+    static const KernelFn prod2[4][4] = {FFR_K_POLICY(0), FFR_K_POLICY(1), FFR_K_POLICY(2), FFR_K_POLICY(3)};
+    static const KernelFn instr2[4] = {FFR_K(2, 0, 2, 2, true), FFR_K(2, 1, 2, 2, true), FFR_K(2, 2, 2, 2, true), FFR_K(2, 3, 2, 2, true)};
+    static const KernelFn prod1[4] = {FFR_K(1, 0, 2, 2, false), FFR_K(1, 1, 2, 2, false), FFR_K(1, 2, 2, 2, false), FFR_K(1, 3, 2, 2, false)};
+    static const KernelFn instr1[4] = {FFR_K(1, 0, 2, 2, true), FFR_K(1, 1, 2, 2, true), FFR_K(1, 2, 2, 2, true), FFR_K(1, 3, 2, 2, true)};
 #undef FFR_K_POLICY
 #undef FFR_K
     KernelFn fn;
@@ -1438,7 +1446,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
         const int slot = current_device_slot();
         std::lock_guard<std::mutex> lock(mu);
         if (!attr_set[slot]) {
-            for (int m = 0; m < 3; ++m) {
+            for (int m = 0; m < 4; ++m) {
                 for (int v = 0; v < 4; ++v)
                     FFR_CUDA_TRY(cudaFuncSetAttribute(prod2[m][v], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
                 FFR_CUDA_TRY(cudaFuncSetAttribute(instr2[m], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -1451,7 +1459,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     const int64_t n_tiles = (n_cand + kTileM * cg - 1) / (kTileM * cg);
     const int64_t max_groups = sms / cg;
     const unsigned grid = static_cast<unsigned>((n_tiles < max_groups ? n_tiles : max_groups) * cg);
-    g_last_cfg[0] = cg; g_last_cfg[1] = p.grid_exact; g_last_cfg[2] = p.grid_updates; g_last_cfg[3] = st32 ? 2 : (fuse ? 1 : 0);
+    g_last_cfg[0] = cg; g_last_cfg[1] = p.grid_exact; g_last_cfg[2] = p.grid_updates; g_last_cfg[3] = nm;
     g_last_cfg[4] = a_stages; g_last_cfg[5] = b_stages; g_last_cfg[6] = static_cast<int>(grid); g_last_cfg[7] = instr ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

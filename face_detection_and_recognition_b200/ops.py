@@ -158,7 +158,7 @@ def face_filter(ref: torch.Tensor, cand: torch.Tensor, thr: float, metric="cosin
                 cfg = (C.c_int32 * 8)()
                 lib.ffr_debug_last_k2_config(cfg)
                 res.stats["k2"] = {"cta_group": cfg[0], "grid_exact": cfg[1], "grid_updates": cfg[2],
-                                   "normalise": ("k1", "fused_scratch", "stage32")[cfg[3]], "a_stages": cfg[4],
+                                   "normalise": ("k1", "fused_scratch", "stage32+tail_offload", "stage32")[cfg[3]], "a_stages": cfg[4],
                                    "b_stages": cfg[5], "grid": cfg[6]}
     return res
 
