@@ -228,8 +228,12 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
         const int n_in = __popc(xm) * ny;                         // candidate columns inside the part (<= 128)
         const int n_all = n_in + (rec.idx2 >= 0 ? 1 : 0);         // + the tracked candidate outside it
         unsigned long long key = 0ull;
-        for (int e0 = 0; e0 < n_all; e0 += 32) {                  // 32 references at a time, one per lane
-            const int e = e0 + lane;
+        // L lanes per reference (the embedding split between them): with the typical 2-8 references of a record most lanes
+        // would idle and every lane would walk a whole row -- four times the dependent L2 round trips
+        const int L = n_all <= 8 ? 4 : (n_all <= 16 ? 2 : 1);
+        const int per = 32 / L, sub = lane % L;
+        for (int e0 = 0; e0 < n_all; e0 += per) {                 // `per` references at a time
+            const int e = e0 + lane / L;
             int64_t ri = -1;
             if (e < n_in) {
                 const int a = __fns(xm, 0, e / ny + 1), b = __fns(ym, 0, e % ny + 1);     // e-th (a, b) pair in ascending column order
@@ -245,14 +249,14 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
                 const float4* r4 = reinterpret_cast<const float4*>(ref + (ri >= 0 ? ri : 0) * dim);
                 const int nq = dim >> 2;
                 constexpr int kU = 8;
-                for (int q0 = 0; q0 < nq; q0 += kU) {
+                for (int q0 = sub; q0 < nq; q0 += kU * L) {
                     float4 rv[kU];
 #pragma unroll
                     for (int u = 0; u < kU; ++u)
-                        rv[u] = (ri >= 0 && q0 + u < nq) ? __ldg(r4 + q0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rv[u] = (ri >= 0 && q0 + u * L < nq) ? __ldg(r4 + q0 + u * L) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
-                        const float4 cv = q0 + u < nq ? c4[q0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 cv = q0 + u * L < nq ? c4[q0 + u * L] : make_float4(0.f, 0.f, 0.f, 0.f);
                         a_acc = fmaf(cv.x, rv[u].x, a_acc); a_acc = fmaf(cv.y, rv[u].y, a_acc);
                         a_acc = fmaf(cv.z, rv[u].z, a_acc); a_acc = fmaf(cv.w, rv[u].w, a_acc);
                         b_acc = fmaf(rv[u].x, rv[u].x, b_acc); b_acc = fmaf(rv[u].y, rv[u].y, b_acc);
@@ -260,11 +264,15 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
                     }
                 }
             } else {
-                for (int q = 0; q < dim; ++q) {
+                for (int q = sub; q < dim; q += L) {
                     const float rvq = ri >= 0 ? __ldg(ref + ri * dim + q) : 0.f;
                     a_acc = fmaf(c_smem[q], rvq, a_acc);
                     b_acc = fmaf(rvq, rvq, b_acc);
                 }
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) {                // the L lanes of a reference hold partial sums
+                a_acc += __shfl_xor_sync(0xffffffffu, a_acc, o);
+                b_acc += __shfl_xor_sync(0xffffffffu, b_acc, o);
             }
             // NOTE: the accumulation order differs from cos_fp32's lane-strided one by fp32 summation noise only (<= ~1e-7); the
             // decision between references that close is fp32-ill-defined anyway (tests: TIE_EPS)
