@@ -45,6 +45,10 @@
 
 #include "ffr_common.cuh"
 
+#ifndef FFR_OOB_CLAMP
+#define FFR_OOB_CLAMP 1
+#endif
+
 namespace ffr {
 
 namespace {
@@ -647,18 +651,29 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 while (s_next < s_total) {
                     if (!mbar_test_wait(&s_empty[sb], sph ^ 1)) return;
                     const int64_t t = tile0 + (s_next / (kTileM / kStageRows)) * tile_stride;
-                    const int32_t r0 = static_cast<int32_t>(t * (kTileM * kCG) + cta_rank * kTileM) +
-                                       static_cast<int32_t>(s_next % (kTileM / kStageRows)) * kStageRows;
-                    mbar_expect_tx(&s_full[sb], kStageBytes);
+                    int32_t r0 = static_cast<int32_t>(t * (kTileM * kCG) + cta_rank * kTileM) +
+                                 static_cast<int32_t>(s_next % (kTileM / kStageRows)) * kStageRows;
+                    // No TMA box may lie ENTIRELY outside its tensor (see the B loads below: such boxes were measured to cost several
+                    // times a normal tile, and crashed one configuration).  Rows past the last candidate are never emitted and the
+                    // normaliser zeroes them (inv = 0): the last in-bounds rows are loaded in their place.  A column group that starts
+                    // at or past `dim` (rows of 68..96 floats) is not loaded at all: the normaliser warps zeroed it once, and nothing
+                    // overwrites it.
+                    if (r0 >= p.n_cand) r0 = p.n_cand > kStageRows ? static_cast<int32_t>(p.n_cand) - kStageRows : 0;
+                    const int n_groups = (p.dim + 31) >> 5;   // live 32-float column groups (3 or 4: dim_pad == 128)
+                    mbar_expect_tx(&s_full[sb], (kStageBytes / 4) * n_groups);
 #pragma unroll
                     for (int g = 0; g < 4; ++g)               // four 32-float (128-byte, swizzled) column groups of the rows
-                        tma_load_2d(smem_s + sb * kStageBytes + g * (kStageBytes / 4), &tmap_cand32, &s_full[sb], g * 32, r0, kEvictFirst);
+                        if (g < n_groups)
+                            tma_load_2d(smem_s + sb * kStageBytes + g * (kStageBytes / 4), &tmap_cand32, &s_full[sb], g * 32, r0, kEvictFirst);
                     ++s_next;
                     if (++sb == static_cast<uint32_t>(p.s_bufs)) { sb = 0; sph ^= 1; }
                 }
             };
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
-                const int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
+                int32_t row0 = static_cast<int32_t>(tile * (kTileM * kCG) + cta_rank * kTileM);
+                // (a fully out-of-bounds A box -- the peer CTA's half of a ragged last tile -- is replaced by the last in-bounds
+                // rows: rows >= n_cand are never emitted)
+                if (row0 >= p.n_cand) row0 = p.n_cand > kTileM ? static_cast<int32_t>(p.n_cand) - kTileM : 0;
                 // The B stream does not depend on the candidate tile: it keeps flowing across tile boundaries, and this
                 // tile's A loads go out the moment their stage is free (and, kNorm, the fp16 rows are written) -- probed
                 // without blocking while the thread waits for B slots.  (Handing A back K-block by K-block during the last
@@ -683,7 +698,13 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (!p.decouple_a && !st32) { while (need_a) try_issue_a(); }      // (A/B knob: the old blocking order)
                 if (!k1_done) { pdl_wait(); k1_done = true; }
                 for (int rt = 0; rt < n_rt; ++rt) {
-                    const int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
+                    int32_t rrow0 = rt * kAccN + static_cast<int32_t>(cta_rank * kBRows);
+                    // A box that lies ENTIRELY past the last reference (the peer CTA's half of a last tile with <= 128 live
+                    // references) is not loaded as such: measured, a tile with such a box costs 4-5 x a normal one (the MMA
+                    // thread waits for b_full ~60 % of its time; cta_group::1, whose box is only partly out of bounds, and 129
+                    // references do not show it).  Its columns are >= n_ref, i.e. masked to -inf by index whatever they hold,
+                    // so the last in-bounds rows are loaded in its place.
+                    if (kCG == 2 && FFR_OOB_CLAMP && rrow0 >= n_ref) rrow0 = n_ref > static_cast<int64_t>(kBRows) ? static_cast<int32_t>(n_ref) - static_cast<int32_t>(kBRows) : 0;
                     for (int kb = 0; kb < p.kb_count; ++kb) {
                         if (need_a) {
                             const long long tw0 = pr ? clock64() : 0;
@@ -809,6 +830,14 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             const uint32_t sw = (static_cast<uint32_t>(lane) & 7u) << 4;                  // this row's swizzle term
             // ---- the epilogue's tail, run here: candidate tile u of this CTA (its state parked by the eight epilogue warps in
             // slot u & 1): each helper warp takes 64 rows, two per lane; merge the column halves (ties -> smaller index), emit.
+            // rows of 68..96 floats: the fourth 32-float column group of every staging buffer is never loaded (a box that lies
+            // entirely past `dim` is not issued); it is zeroed here once -- both warps write the same zeros, so each sees its own
+            if (((p.dim + 31) >> 5) < 4) {
+                for (int b = 0; b < p.s_bufs; ++b)
+                    for (int i = lane; i < static_cast<int>(kStageBytes / 4 / 16); i += 32)
+                        reinterpret_cast<uint4*>(smem_s + b * kStageBytes + 3 * (kStageBytes / 4))[i] = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+            }
             bool k1_waited = false;
             auto merge_tile = [&](uint32_t u) {
                 const long long tm0 = pr ? clock64() : 0;
