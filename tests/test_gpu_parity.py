@@ -533,3 +533,23 @@ def test_duplicate_heavy_gallery_is_folded(ops, ffr_env, n_ref, n_cand, dim, cop
     gap, _ = _top2_gap64(np.unique(ref, axis=0), cand[small][:2000])
     ok = torch.from_numpy(gap > TIE_EPS).to(dev)
     assert torch.equal(r0.best_idx[:2000][ok], r1.best_idx[:2000][ok]) and torch.equal(r0.keep[:2000], r1.keep[:2000])
+
+
+# ---------------------------------------------------------------- small galleries through the fused stage32 schedule (round 2)
+@pytest.mark.parametrize("n_ref,n_cand,dim,offload", [
+    (128, 75_776 + 77, 128, "auto"), (128, 113_704, 128, "1"), (64, 76_000, 72, "auto"), (32, 80_000, 128, "1"),
+    (300, 80_000, 100, "auto"), (384, 77_000, 128, "auto"), (384, 77_000, 128, "0"), (129, 76_001, 96, "1"), (200, 151_552 + 129, 128, "auto")])
+def test_small_galleries_fused(ops, ffr_env, n_ref, n_cand, dim, offload):
+    """<= 128 live references in a tile leave the peer CTA's half of the B tile (and, for ragged candidate counts, of the A /
+    staging boxes) entirely past the end of its tensor.  Such TMA boxes are never issued as they stand (measured: 4-5 x the
+    tile time, and a launch failure with the offloaded tail): the last in-bounds rows are loaded instead, dead column groups
+    (rows of 68..96 floats) are zeroed once.  Both forms of the stage32 tail, exact parity bar."""
+    if offload != "auto":
+        ffr_env.setenv("FFR_TAIL_OFFLOAD", offload)
+    ref, cand = oracle.make_synthetic(n_ref, n_cand, dim, seed=n_ref + dim, n_adversarial=300, n_dup_refs=min(8, n_ref // 4),
+                                      unit_norm=False)
+    rng = np.random.default_rng(1)
+    sample = rng.choice(n_cand, 6000, replace=False)
+    sample = np.unique(np.concatenate([sample, np.arange(n_cand - 300, n_cand)]))          # the ragged tail in full
+    res = _check_cosine(ops, ref, cand, 0.5, sample=sample)
+    assert res.stats["k2"]["normalise"].startswith("stage32"), res.stats
