@@ -45,12 +45,15 @@ extern "C" {
 #define FFR_METRIC_EUCLID 1      /* best = min_i |c - r_i|,          keep = best <= thr  (filter_faces...:189, extract_and_label...:104) */
 
 #define FFR_DTYPE_F32 0          /* raw fp32 embeddings; the op normalises internally */
-#define FFR_DTYPE_F16 1          /* rows already L2-normalised + converted by ffr_l2norm_rows_f32 (leading dim = ffr_padded_dim) */
+#define FFR_DTYPE_F16 1          /* rows already L2-normalised + converted by ffr_l2norm_rows_f32 (leading dim = ffr_padded_dim).
+                                    There are no fp32 rows to re-check against: keep / best_idx are then exact in fp16-OPERAND space
+                                    (the index carries the row's largest fp16-operand score, ties -> first), i.e. they can differ from
+                                    the fp32 decision for pairs closer than ~1.5e-4; best_val is within 1e-3 as always */
 
 /* flags for ffr_filter_ex */
 #define FFR_FLAG_FORCE_FP32   1  /* use the exact fp32 CUDA-core kernel whatever the shape */
 #define FFR_FLAG_FORCE_MMA    2  /* use the tcgen05 kernel (cosine, dim <= 512) whatever n_ref */
-#define FFR_FLAG_NO_RECHECK   4  /* skip the fp32 re-check of near-tie / near-threshold rows (benchmarking only) */
+#define FFR_FLAG_NO_RECHECK   4  /* skip the fp32 re-check of near-tie / near-threshold rows (benchmarking only): decisions as for FFR_DTYPE_F16 */
 
 typedef void* ffr_stream_t;      /* cudaStream_t */
 typedef struct ffr_ctx  ffr_ctx; /* host-buffer pipeline context (streams, staging, workspace) */
@@ -86,7 +89,10 @@ int ffr_l2norm_rows_f32(const float* x, int64_t rows, int32_t dim,
  *   ref_index_base added to every best_idx (global index of ref row 0)
  *   keep u8[n_cand], best_idx i32[n_cand], best_val f32[n_cand]   device outputs (best_val may be NULL)
  * ffr_filter_ex additionally lists the tolerance band: rows with |best - thr| <= band_tol are appended
- * (unordered) to band_rows[0..band_cap) and counted in *band_count (device int32; count may exceed cap). */
+ * (unordered) to band_rows[0..band_cap) and counted in *band_count (device int32; count may exceed cap); `best` is the
+ * fp32 re-checked score, or the fp16-operand score where no re-check runs (FFR_DTYPE_F16, FFR_FLAG_NO_RECHECK).
+ * Bit-identical reference rows are folded internally (a later copy can never be the first arg-best); best_idx always
+ * refers to the caller's row numbering. */
 size_t ffr_filter_workspace_bytes(int64_t n_ref, int64_t n_cand, int32_t dim, int dtype, int metric);
 
 int ffr_filter(const void* ref, int64_t n_ref, const void* cand, int64_t n_cand, int32_t dim, int dtype,
