@@ -89,6 +89,8 @@ const Knobs* read_knobs() {
     k->dedup_refs = env_int("FFR_DEDUP_REFS", 1);
     k->tail_offload = env_int("FFR_TAIL_OFFLOAD", -1);
     k->pdl = env_int("FFR_PDL", 1);
+    k->cand_l2_mb = env_int("FFR_CAND_L2_MB", 0);      // stage32: candidate matrices up to this size (MiB) are loaded WITHOUT evict-first (measured: slower)
+    k->k3_skip = env_int("FFR_K3_SKIP", 0);            // timing experiments: K3 phases left out (1 pairs, 2 parts, 4 full) -- WRONG results
     return k;
 }
 }  // namespace

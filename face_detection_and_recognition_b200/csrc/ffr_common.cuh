@@ -39,18 +39,18 @@ constexpr int kMaxDevices = 64;
 struct Knobs {
     int cta_group, a_stages, b_stages, acc_stages, diag_half_b, epi_mode, discard_a, decouple_a,
         norm_evict_first, norm_diag, grid_update_refs, grid_exact, norm_ahead, fuse_k1, stage32, k1_blocks_per_sm,
-        k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, tail_offload, pdl;
+        k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, tail_offload, pdl, cand_l2_mb, k3_skip;
 };
 const Knobs& knobs();
 void reload_knobs();
 float recheck_delta();                                     // K3 window in cosine units; test hook can change it
 
 // ---- layout of the per-row recheck record K2 -> K3 ------------------------------------------------
-struct RecheckRec {
-    int32_t row;        // candidate row (local)
-    int32_t idx1;       // best reference (local index), fp16-score space
-    int32_t idx2;       // runner-up reference, or -1
-    int32_t idx3;       // third reference inside the window, or -1
+struct RecheckRec {     // pair record (K3a)                                  | part record (K3p, written from the END of the array)
+    int32_t row;        // candidate row (local)                              | same
+    int32_t idx1;       // best reference (local index), fp16-score space     | (first compact column of the span >> 7) | Y-group mask << 24
+    int32_t idx2;       // runner-up reference, or -1                         | one tracked candidate outside the span, or -1
+    int32_t idx3;       // third reference inside the window, or -1           | X-group mask: 16 bits per 128-column part (one or two adjacent parts)
 };
 
 // rows whose third-best score is also within delta: rescanned against every reference in fp32 (K3b).

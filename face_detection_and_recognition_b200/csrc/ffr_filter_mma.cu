@@ -87,6 +87,50 @@ struct Hidden {
                         // reached the window floor when the part was seen -- its in-window columns are among {8a + b}
 };
 
+// The two column halves of a candidate row merged (end of the candidate tile).  Their leading parts are joined into ONE span
+// when they are ADJACENT (first columns 128 apart: the two halves of one reference tile, or the upper half of one and the
+// lower half of the next) -- a group of near-identical references that straddles a part boundary puts several in-window columns
+// into both, and without this every such row went to the full rescan.  xm: X-group bits of the span's first part in bits
+// 0-15, of its second part (if any) in bits 16-31; ym: the union of their Y-group bits (a superset of the in-window columns).
+struct HiddenM {
+    float amb, amb2;
+    int32_t base;       // first column of the span
+    uint32_t xm, ym;
+};
+
+__device__ __forceinline__ HiddenM hidden_single(const Hidden& a) {
+    HiddenM m;
+    m.amb = a.amb; m.amb2 = a.amb2; m.base = a.base;
+    m.xm = static_cast<uint32_t>(a.mask) & 0xFFFFu;
+    m.ym = (static_cast<uint32_t>(a.mask) >> 16) & 0xFFu;
+    return m;
+}
+
+__device__ __forceinline__ HiddenM hidden_merge(const Hidden& a, const Hidden& b) {
+    constexpr int32_t kPart = kTileN / 2;
+    const bool both = a.amb > -INFINITY && b.amb > -INFINITY;
+    const bool a_first = a.base < b.base;
+    const int32_t gap = a_first ? b.base - a.base : a.base - b.base;
+    const uint32_t xa = static_cast<uint32_t>(a.mask) & 0xFFFFu, xb = static_cast<uint32_t>(b.mask) & 0xFFFFu;
+    const uint32_t ya = (static_cast<uint32_t>(a.mask) >> 16) & 0xFFu, yb = (static_cast<uint32_t>(b.mask) >> 16) & 0xFFu;
+    HiddenM m;
+    if (both && gap == kPart) {                        // adjacent: one span of two parts, nothing "hidden elsewhere" added
+        m.amb = fmaxf(a.amb, b.amb);
+        m.amb2 = fmaxf(a.amb2, b.amb2);
+        m.base = a_first ? a.base : b.base;
+        m.xm = a_first ? (xa | (xb << 16)) : (xb | (xa << 16));
+        m.ym = ya | yb;
+    } else {                                           // the larger part maximum leads, the other is "a second part"
+        const bool b_leads = b.amb > a.amb;
+        m.amb = fmaxf(a.amb, b.amb);
+        m.amb2 = fmax3(a.amb2, b.amb2, fminf(a.amb, b.amb));
+        m.base = b_leads ? b.base : a.base;
+        m.xm = b_leads ? xb : xa;
+        m.ym = b_leads ? yb : ya;
+    }
+    return m;
+}
+
 __device__ __forceinline__ void top3_insert(Top3& t, float v, int32_t idx) {
     const bool g1 = v > t.b1, g2 = v > t.b2, g3 = v > t.b3, g4 = v > t.b4;
     t.b4 = g3 ? t.b3 : (g4 ? v : t.b4);
@@ -420,6 +464,8 @@ struct KParams {
                                    // warps write the swizzled fp16 A tile directly (no global scratch, no K1 pass at ANY n_ref)
     int s_bufs;                    // stage32: staging ring depth (buffers of kStageRows rows)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
+    uint64_t cand32_policy;        // stage32: L2 policy of the fp32 candidate loads -- evict-first for a stream larger than L2, plain when the
+                                   // whole candidate matrix fits (K3's fp32 re-check then finds its rows in L2 instead of HBM)
     uint32_t b_tx_bytes;           // bytes one CTA's B-stage TMA load delivers (diagnostics can halve the box: FFR_DIAG_HALF_B)
     int epi_mode;                  // diagnostics: 1 = epilogue only loads TMEM (no max tree), results invalid
     unsigned long long* prof;      // optional [gridDim.x][32] stall-cycle counters (diagnostics)
@@ -437,7 +483,7 @@ struct RowOut {
     RecheckRec rec;
 };
 
-__device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, const Hidden& hid, int64_t row) {
+__device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, const HiddenM& hid, int64_t row) {
     RowOut o;
     const bool valid = row < p.n_cand;
     const bool near_tie = (t.i2 >= 0) && (t.b1 - t.b2 <= p.delta);
@@ -464,10 +510,12 @@ __device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, 
     o.rec.idx1 = o.rec.idx2 = o.rec.idx3 = -1;
     if (o.cls == 2) {
         // The part's own placeholder entry (and anything else inside the part) is covered by K3's scan of the part.  The record
-        // names the part by its first COMPACT column and carries the X / Y group masks (the in-window columns are among
-        // {8a + b}) plus ONE tracked candidate outside the part, by original index; a second one makes it a full rescan.
+        // names the span (one part or two adjacent ones) by its first COMPACT column and carries the X / Y group masks (the
+        // in-window columns are among {8a + b}) plus ONE tracked candidate outside the span, by original index; a second one
+        // makes it a full rescan.  (Layout: ffr_recheck.cu, K3p.)
+        const int32_t span = (hid.xm >> 16) != 0u ? kTileN : kTileN / 2;     // one part, or two adjacent ones
         const auto outside = [&](float b, int32_t i) {
-            return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + kTileN / 2);
+            return i >= 0 && b >= t.b1 - p.delta && (i < hid.base || i >= hid.base + span);
         };
         int32_t e = -1;
         int ne = 0;
@@ -475,9 +523,9 @@ __device__ __forceinline__ RowOut classify_row(const KParams& p, const Top3& t, 
         if (outside(t.b2, t.i2)) { e = ne ? e : t.i2; ++ne; }
         if (outside(t.b3, t.i3)) { e = ne ? e : t.i3; ++ne; }
         if (ne > 1) o.cls = 3;
-        o.rec.idx1 = hid.base;
+        o.rec.idx1 = static_cast<int32_t>(static_cast<uint32_t>(hid.base >> 7) | (hid.ym << 24));   // (base: a multiple of 128, < 2^31)
         o.rec.idx2 = orig(e);
-        o.rec.idx3 = hid.mask;
+        o.rec.idx3 = static_cast<int32_t>(hid.xm);
     } else if (o.cls == 1) {
         o.rec.idx1 = orig(t.i1);
         o.rec.idx2 = near_tie ? orig(t.i2) : -1;
@@ -664,7 +712,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                     for (int g = 0; g < 4; ++g)               // four 32-float (128-byte, swizzled) column groups of the rows
                         if (g < n_groups)
-                            tma_load_2d(smem_s + sb * kStageBytes + g * (kStageBytes / 4), &tmap_cand32, &s_full[sb], g * 32, r0, kEvictFirst);
+                            tma_load_2d(smem_s + sb * kStageBytes + g * (kStageBytes / 4), &tmap_cand32, &s_full[sb], g * 32, r0, p.cand32_policy);
                     ++s_next;
                     if (++sb == static_cast<uint32_t>(p.s_bufs)) { sb = 0; sph ^= 1; }
                 }
@@ -863,18 +911,16 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     hid.mask = __float_as_int(ma[10 * kTileM + r]);
                     const float o1 = mb[0 * kTileM + r], o2 = mb[1 * kTileM + r], o3 = mb[2 * kTileM + r], o4 = mb[3 * kTileM + r];
                     const int32_t j1 = __float_as_int(mb[4 * kTileM + r]), j2 = __float_as_int(mb[5 * kTileM + r]), j3 = __float_as_int(mb[6 * kTileM + r]);
-                    const float o_amb = mb[7 * kTileM + r], o_amb2 = mb[8 * kTileM + r];
-                    const int32_t o_base = __float_as_int(mb[9 * kTileM + r]);
-                    const int32_t o_mask = __float_as_int(mb[10 * kTileM + r]);
-                    hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
-                    hid.base = o_amb > hid.amb ? o_base : hid.base;
-                    hid.mask = o_amb > hid.amb ? o_mask : hid.mask;
-                    hid.amb = fmaxf(hid.amb, o_amb);
+                    Hidden hio;
+                    hio.amb = mb[7 * kTileM + r]; hio.amb2 = mb[8 * kTileM + r];
+                    hio.base = __float_as_int(mb[9 * kTileM + r]);
+                    hio.mask = __float_as_int(mb[10 * kTileM + r]);
+                    const HiddenM hm = hidden_merge(hid, hio);
                     if (o1 != -INFINITY) top3_merge_insert(t, o1, j1);
                     if (j2 >= 0) top3_merge_insert(t, o2, j2);
                     if (j3 >= 0) top3_merge_insert(t, o3, j3);
                     t.b4 = fmaxf(t.b4, o4);
-                    ro[rr] = classify_row(p, t, hid, tile_u * (kTileM * kCG) + cta_rank * kTileM + r);
+                    ro[rr] = classify_row(p, t, hm, tile_u * (kTileM * kCG) + cta_rank * kTileM + r);
                 }
                 // the slot's contents are in registers: hand it back before the list appends (their atomics are the slow part)
                 __syncwarp();
@@ -1210,6 +1256,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (pr) c_bar1 += static_cast<unsigned long long>(clock64() - tm0);
                 float ob[kParts - 1][4];
                 int32_t oi[kParts - 1][3];
+                static_assert(kParts == 2, "hidden_merge joins the states of TWO column halves");
+                HiddenM hm = hidden_single(hid);
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
                     const float* mg = merge + pp * 11 * kTileM;
@@ -1217,14 +1265,12 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
 #pragma unroll
                     for (int e = 0; e < 3; ++e) oi[pp][e] = __float_as_int(mg[(4 + e) * kTileM + r_in_tile]);
-                    // the other half's hidden-column state: the larger part maximum leads, everything else is "a second part"
-                    const float o_amb = mg[7 * kTileM + r_in_tile], o_amb2 = mg[8 * kTileM + r_in_tile];
-                    const int32_t o_base = __float_as_int(mg[9 * kTileM + r_in_tile]);
-                    const int32_t o_mask = __float_as_int(mg[10 * kTileM + r_in_tile]);
-                    hid.amb2 = fmax3(hid.amb2, o_amb2, fminf(hid.amb, o_amb));
-                    hid.base = o_amb > hid.amb ? o_base : hid.base;
-                    hid.mask = o_amb > hid.amb ? o_mask : hid.mask;
-                    hid.amb = fmaxf(hid.amb, o_amb);
+                    // the other half's hidden-column state (hidden_merge: adjacent parts are joined, else the larger maximum leads)
+                    Hidden hio;
+                    hio.amb = mg[7 * kTileM + r_in_tile]; hio.amb2 = mg[8 * kTileM + r_in_tile];
+                    hio.base = __float_as_int(mg[9 * kTileM + r_in_tile]);
+                    hio.mask = __float_as_int(mg[10 * kTileM + r_in_tile]);
+                    hm = hidden_merge(hid, hio);
                 }
                 if (!kAlt) named_bar_arrive(5 + q, kParts * 32);
 #pragma unroll
@@ -1236,7 +1282,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 }
 
                 RowOut ro[1];
-                ro[0] = classify_row(p, t, hid, row);
+                ro[0] = classify_row(p, t, hm, row);
                 append_rows<1>(p, ro, lane);
             }
             }   // !st32
@@ -1440,6 +1486,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.decouple_a = kn.decouple_a;
     p.stage32 = st32 ? 1 : 0;
     p.s_bufs = s_bufs;
+    p.cand32_policy = static_cast<double>(n_cand) * dim * 4.0 <= kn.cand_l2_mb * 1048576.0 ? kEvictNormal : kEvictFirst;
     p.norm_evict_first = kn.norm_evict_first;
     p.norm_diag = kn.norm_diag;
     p.grid_updates = n_ref <= kn.grid_update_refs ? 1 : 0;

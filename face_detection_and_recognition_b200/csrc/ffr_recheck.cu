@@ -117,15 +117,71 @@ recheck_pairs_phase(float* s_rows, const float* __restrict__ ref, const float* _
                     int64_t* band_rows, int64_t band_cap, bool vec) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* c_smem = s_rows + static_cast<size_t>(w) * dim;
-    int64_t count = lists.hdr->recheck_count;
-    if (count > lists.rec_cap) count = lists.rec_cap;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
+    // the warp's first record is requested TOGETHER with the list length, not after it (it is only used when it exists):
+    // with a short list the phase is one chain of dependent memory latencies, and this takes one L2 round trip out of it
+    RecheckRec rec0{};
+    if (warp < lists.rec_cap) rec0 = lists.recs[warp];
+    int64_t count = lists.hdr->recheck_count;
+    if (count > lists.rec_cap) count = lists.rec_cap;
     // The candidate row of the NEXT record is fetched into registers (an HBM miss, ~1.5 us) while the current one is
     // scored, and the up-to-three references of a record are scored together (one L2 round trip): a warp's rows used to
     // cost three or four dependent memory latencies each.
     const bool pipe = vec && dim <= 512;
     const int nvec = dim >> 2;
+    if (vec && nvec <= 32) {
+        // Rows of <= 128 floats: ONE float4 per lane and row, everything in registers.  With a short list (BASELINE configs[1]:
+        // one record per warp) the phase is a chain of dependent memory latencies, so it is made as short as it gets: the
+        // candidate row (HBM) and the up-to-three reference rows (L2) are requested together.  Same arithmetic as cos_fp32 / the parked-row form below, bit for bit.
+        int64_t k = warp;
+        RecheckRec rec = rec0;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* cand4 = reinterpret_cast<const float4*>(cand);
+        const float4* ref4 = reinterpret_cast<const float4*>(ref);
+        while (k < count) {
+            const bool live = lane < nvec;
+            const int32_t i2 = rec.idx2 >= 0 ? rec.idx2 : rec.idx1;
+            const int32_t i3 = rec.idx3 >= 0 ? rec.idx3 : i2;
+            const float4 cv = live ? __ldg(cand4 + static_cast<int64_t>(rec.row) * nvec + lane) : z4;
+            float4 rv[3];
+            rv[0] = live ? __ldg(ref4 + static_cast<int64_t>(rec.idx1) * nvec + lane) : z4;
+            rv[1] = live ? __ldg(ref4 + static_cast<int64_t>(i2) * nvec + lane) : z4;
+            rv[2] = live ? __ldg(ref4 + static_cast<int64_t>(i3) * nvec + lane) : z4;
+            const int64_t k_next = k + nwarps;
+            RecheckRec rec_next = rec;
+            if (k_next < count) rec_next = lists.recs[k_next];
+            float cc = 0.f;
+            cc = fmaf(cv.x, cv.x, cc); cc = fmaf(cv.y, cv.y, cc); cc = fmaf(cv.z, cv.z, cc); cc = fmaf(cv.w, cv.w, cc);
+            float a[3], b[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                a[r] = 0.f; b[r] = 0.f;
+                a[r] = fmaf(cv.x, rv[r].x, a[r]); a[r] = fmaf(cv.y, rv[r].y, a[r]);
+                a[r] = fmaf(cv.z, rv[r].z, a[r]); a[r] = fmaf(cv.w, rv[r].w, a[r]);
+                b[r] = fmaf(rv[r].x, rv[r].x, b[r]); b[r] = fmaf(rv[r].y, rv[r].y, b[r]);
+                b[r] = fmaf(rv[r].z, rv[r].z, b[r]); b[r] = fmaf(rv[r].w, rv[r].w, b[r]);
+            }
+            const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { a[r] = warp_sum(a[r]); b[r] = warp_sum(b[r]); }
+            float sc[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) sc[r] = __fdiv_rn(a[r], __fmul_rn(__fsqrt_rn(b[r]), cc_sqrt));
+            float best = sc[0];
+            int32_t bi = rec.idx1;
+            if (rec.idx2 >= 0) {
+                if (sc[1] > best || (sc[1] == best && rec.idx2 < bi)) { best = sc[1]; bi = rec.idx2; }
+                if (rec.idx3 >= 0 && (sc[2] > best || (sc[2] == best && rec.idx3 < bi))) { best = sc[2]; bi = rec.idx3; }
+            }
+            if (lane == 0)
+                emit_result(rec.row, best, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol, band_count,
+                            band_rows, band_cap);
+            k = k_next;
+            rec = rec_next;
+        }
+        return;
+    }
     float4 pre[4];
     RecheckRec rec{}, rec_next{};
     int64_t k = warp;
@@ -134,7 +190,7 @@ recheck_pairs_phase(float* s_rows, const float* __restrict__ ref, const float* _
 #pragma unroll
         for (int j = 0; j < 4; ++j) pre[j] = (lane + 32 * j < nvec) ? __ldg(c4 + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (k < count) { rec = lists.recs[k]; if (pipe) prefetch(rec); }
+    if (k < count) { rec = rec0; if (pipe) prefetch(rec); }
     while (k < count) {
         float cc = 0.f;
         __syncwarp();
@@ -194,12 +250,13 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float& v, int32
 }
 
 // K3p: rows whose un-inserted in-window columns all lie in ONE 128-reference part of K2's column grid (flag-only update path,
-// DESIGN.md section 4).  The record names the part (first compact column), the X groups (columns 8a..8a+7, 16 bits) and Y groups
-// (column mod 8, 8 bits) that reached the window floor -- the in-window columns are among {8a + b} -- and one tracked
-// candidate outside the part.  fp32 cosine against exactly those references; first occurrence of the maximum.  One warp per
-// record, LANE PER REFERENCE (the candidate row broadcast from shared memory): no shuffles until the final argmax merge,
-// every lane streams its own reference row out of L2.  Typically 2-8 references, at most 129.
-constexpr int kPartRefs = 128;          // == kTileN / 2 of ffr_filter_mma.cu (one epilogue warp's columns of a reference tile)
+// DESIGN.md section 4) -- or in TWO ADJACENT parts (a group of near-identical references that straddles a part boundary: the two
+// parts are seen by the two column halves of K2's epilogue and joined when their states are merged).  Record: idx1 = (first
+// compact column of the first part >> 7) | Y-group mask << 24, idx3 = X-group mask, 16 bits per part (bit a: columns
+// 8a..8a+7 of the 256-column span; Y bit b: column mod 8 == b) -- the in-window columns are among {8a + b} -- and idx2 = one
+// tracked candidate outside the span.  fp32 cosine against exactly those references; first occurrence of the maximum.  One
+// warp per record, L LANES PER REFERENCE (the candidate row broadcast from shared memory).  Typically 2-8 references.
+__device__ __forceinline__ int64_t parts_first_item(int64_t warp, int64_t nwarps) { return nwarps - 1 - warp; }
 
 __device__ __forceinline__ void
 recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
@@ -209,42 +266,53 @@ recheck_parts_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref,
                     const int32_t* __restrict__ n_unique_dev) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float* c_smem = s_rows + static_cast<size_t>(w) * dim;
+    // records are dealt from the LAST warp of the grid downwards: with a short pairs list (dealt from warp 0 upwards) the two
+    // phases then run on different warps at the same time instead of one after the other on the same ones
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
+    const int64_t warp = parts_first_item(static_cast<int64_t>(blockIdx.x) * kWarps + w, nwarps);
+    RecheckRec rec0{};                                            // requested together with the count (see the pairs phase)
+    if (warp < lists.rec_cap) rec0 = lists.recs[lists.rec_cap - 1 - warp];
     // duplicate references folded before K2: the part is a range of COMPACT columns (ref_map: column -> original reference)
     const int64_t n_cols = n_unique_dev != nullptr ? static_cast<int64_t>(__ldg(n_unique_dev)) : n_ref;
     int64_t count = lists.hdr->part_count;
     if (count > lists.rec_cap) count = lists.rec_cap;
-    const int64_t warp = static_cast<int64_t>(blockIdx.x) * kWarps + w;
-    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
     for (int64_t k = warp; k < count; k += nwarps) {
-        const RecheckRec rec = lists.recs[lists.rec_cap - 1 - k];
-        const float* c = cand + static_cast<int64_t>(rec.row) * dim;
-        float cc = 0.f;
-        __syncwarp();
-        for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
-        __syncwarp();
-        const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
-        const uint32_t xm = static_cast<uint32_t>(rec.idx3) & 0xFFFFu, ym = (static_cast<uint32_t>(rec.idx3) >> 16) & 0xFFu;
+        const RecheckRec rec = k == warp ? rec0 : lists.recs[lists.rec_cap - 1 - k];
+        const uint32_t xm = static_cast<uint32_t>(rec.idx3), ym = static_cast<uint32_t>(rec.idx1) >> 24;
+        const int64_t col0 = static_cast<int64_t>(static_cast<uint32_t>(rec.idx1) & 0xFFFFFFu) << 7;   // first compact column of the (first) part
         const int ny = __popc(ym);
-        const int n_in = __popc(xm) * ny;                         // candidate columns inside the part (<= 128)
+        const int n_in = __popc(xm) * ny;                         // candidate columns inside the part(s) (<= 256)
         const int n_all = n_in + (rec.idx2 >= 0 ? 1 : 0);         // + the tracked candidate outside it
         unsigned long long key = 0ull;
         // L lanes per reference (the embedding split between them): with the typical 2-8 references of a record most lanes
         // would idle and every lane would walk a whole row -- four times the dependent L2 round trips
         const int L = n_all <= 8 ? 4 : (n_all <= 16 ? 2 : 1);
         const int per = 32 / L, sub = lane % L;
-        for (int e0 = 0; e0 < n_all; e0 += per) {                 // `per` references at a time
-            const int e = e0 + lane / L;
-            int64_t ri = -1;
+        // the reference this lane scores in batch eb of `per` references (-1: none)
+        auto ref_of = [&](int eb) -> int64_t {
+            const int e = eb * per + lane / L;
             if (e < n_in) {
                 const int a = __fns(xm, 0, e / ny + 1), b = __fns(ym, 0, e % ny + 1);     // e-th (a, b) pair in ascending column order
-                const int64_t col = static_cast<int64_t>(rec.idx1) + 8 * a + b;
-                if (col < n_cols) ri = ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + col)) : col;
-            } else if (e == n_in && rec.idx2 >= 0) {
-                ri = rec.idx2;
+                const int64_t col = col0 + 8 * a + b;
+                if (col < n_cols) return ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + col)) : col;
+                return -1;
             }
+            return (e == n_in && rec.idx2 >= 0) ? static_cast<int64_t>(rec.idx2) : -1;
+        };
+        const float* c = cand + static_cast<int64_t>(rec.row) * dim;
+        float cc = 0.f;
+        __syncwarp();
+        for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); c_smem[d] = t; cc = fmaf(t, t, cc); }
+        __syncwarp();
+        const float cc_sqrt = __fsqrt_rn(warp_sum(cc));
+        for (int e0 = 0, eb = 0; e0 < n_all; e0 += per, ++eb) {   // `per` references at a time
+            const int64_t ri = ref_of(eb);
             float a_acc = 0.f, b_acc = 0.f;
             if (vec) {
-                // eight float4 steps at a time, every load issued before the first FMA: the rows come out of L2 (~600 cycles)
+                // eight float4 steps at a time, every load issued before the first FMA: the rows come out of L2 (~600 cycles).
+                // (A software pipeline across batches -- next batch's loads before this batch's FMAs -- was measured: nothing at
+                // BASELINE configs[1], where the phase is latency-bound but runs beside the others, and 4 % SLOWER with a million
+                // records, where sixteen warps per SM hide the latency and the register copies are pure cost.)
                 const float4* c4 = reinterpret_cast<const float4*>(c_smem);
                 const float4* r4 = reinterpret_cast<const float4*>(ref + (ri >= 0 ? ri : 0) * dim);
                 const int nq = dim >> 2;
@@ -312,6 +380,12 @@ constexpr int kSmallBatch = 8;       // latency, and 32-reference items meant fo
 // reference read): only worth it while that is a few tens of MB of L2 traffic
 constexpr long long kSmallElems = 16000000;
 
+// (runs are dealt starting in the MIDDLE of the grid: away from the warps that hold the first pair and part records)
+__device__ __forceinline__ int64_t small_first_item(int64_t warp, int64_t nwarps, int64_t ipw) {
+    const int64_t half = nwarps >> 1;
+    return (warp >= half ? warp - half : warp + (nwarps - half)) * ipw;
+}
+
 __device__ __forceinline__ void
 rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, const float* __restrict__ cand, int32_t dim,
                    float thr, int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
@@ -326,7 +400,7 @@ rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, 
     // every warp takes a CONTIGUOUS run of items: consecutive reference blocks of the same row, so the row is parked once
     // and the warp merges its blocks in registers -- one atomicMax + one counter update per (warp, row), not per item
     const int64_t ipw = (n_items + nwarps - 1) / nwarps;
-    const int64_t i0 = warp * ipw;
+    const int64_t i0 = small_first_item(warp, nwarps, ipw);
     const int64_t i1 = (i0 + ipw < n_items) ? i0 + ipw : n_items;
     int64_t cur = -1;
     int32_t pending = 0;
@@ -353,6 +427,56 @@ rescan_small_phase(float* s_rows, const float* __restrict__ ref, int64_t n_ref, 
                         band_count, band_rows, band_cap);
         }
     };
+    const int nvec = dim >> 2;
+    if (vec && nvec <= 32) {
+        // rows of <= 128 floats: one float4 per lane and row, all in registers, and the item's reference rows (which need no
+        // list entry to be named) are requested BEFORE the candidate row's index is even known -- the phase is a chain of
+        // memory latencies.  Same arithmetic as cos_fp32, bit for bit.
+        static_assert(kSmallRefs == kSmallBatch, "one batch per item");
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* ref4 = reinterpret_cast<const float4*>(ref);
+        const bool live = lane < nvec;
+        float4 cv = z4;
+        for (int64_t item = i0; item < i1; ++item) {
+            const int64_t slot = item / nb, blk = item - slot * nb;
+            const int64_t lo = blk * kSmallRefs;
+            const int n_rows = static_cast<int>(n_ref - lo < kSmallRefs ? n_ref - lo : kSmallRefs);
+            float4 rv[kSmallBatch];
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r)
+                rv[r] = live ? __ldg(ref4 + (lo + (r < n_rows ? r : n_rows - 1)) * nvec + lane) : z4;
+            if (slot != cur) {
+                flush();
+                cv = live ? __ldg(reinterpret_cast<const float4*>(cand) + static_cast<int64_t>(lists.full_rows[slot]) * nvec + lane) : z4;
+                float cc = 0.f;
+                cc = fmaf(cv.x, cv.x, cc); cc = fmaf(cv.y, cv.y, cc); cc = fmaf(cv.z, cv.z, cc); cc = fmaf(cv.w, cv.w, cc);
+                cc_sqrt = __fsqrt_rn(warp_sum(cc));
+                cur = slot;
+                pending = 0;
+                best = -INFINITY;
+                bi = 0x7FFFFFFF;
+            }
+            float a[kSmallBatch], b[kSmallBatch];
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r) {
+                a[r] = 0.f; b[r] = 0.f;
+                a[r] = fmaf(cv.x, rv[r].x, a[r]); a[r] = fmaf(cv.y, rv[r].y, a[r]);
+                a[r] = fmaf(cv.z, rv[r].z, a[r]); a[r] = fmaf(cv.w, rv[r].w, a[r]);
+                b[r] = fmaf(rv[r].x, rv[r].x, b[r]); b[r] = fmaf(rv[r].y, rv[r].y, b[r]);
+                b[r] = fmaf(rv[r].z, rv[r].z, b[r]); b[r] = fmaf(rv[r].w, rv[r].w, b[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r) { a[r] = warp_sum(a[r]); b[r] = warp_sum(b[r]); }
+#pragma unroll
+            for (int r = 0; r < kSmallBatch; ++r) {              // ascending + strict '>' = first occurrence
+                const float sc = __fdiv_rn(a[r], __fmul_rn(__fsqrt_rn(b[r]), cc_sqrt));
+                if (r < n_rows && sc > best) { best = sc; bi = static_cast<int32_t>(lo + r); }
+            }
+            ++pending;
+        }
+        flush();
+        return;
+    }
     for (int64_t item = i0; item < i1; ++item) {
         const int64_t slot = item / nb, blk = item - slot * nb;
         if (slot != cur) {
@@ -391,17 +515,20 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
                int64_t ref_index_base, uint8_t* __restrict__ keep, int32_t* __restrict__ best_idx,
                float* __restrict__ best_val, RecheckLists lists, float band_tol, int32_t* band_count,
                int64_t* band_rows, int64_t band_cap, const int32_t* __restrict__ ref_map,
-               const int32_t* __restrict__ n_unique_dev) {
+               const int32_t* __restrict__ n_unique_dev, int skip) {
     extern __shared__ __align__(16) float s_c[];               // kFullGroup x dim candidate rows | staged reference tile
     __shared__ float s_ccs[kFullGroup];
     __shared__ unsigned long long s_key[kWarps][kFullGroup];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     pdl_wait();                 // launched as K2's programmatic dependent: everything below reads K2's lists and outputs
-    recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
-                        band_rows, band_cap, kVec);
-    recheck_parts_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
-                        band_rows, band_cap, kVec, ref_map, n_unique_dev);
+    if (!(skip & 1))
+        recheck_pairs_phase(s_c, ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
+                            band_rows, band_cap, kVec);
+    if (!(skip & 2))
+        recheck_parts_phase(s_c, ref, n_ref, cand, dim, thr, ref_index_base, keep, best_idx, best_val, lists, band_tol, band_count,
+                            band_rows, band_cap, kVec, ref_map, n_unique_dev);
+    if (skip & 4) return;
     int64_t count = lists.hdr->full_count;
     if (count > lists.full_cap) count = lists.full_cap;
     if (count == 0) return;
@@ -644,10 +771,11 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (knobs().pdl & 2) != 0 ? 1 : 0;        // FFR_PDL bit 1 (bit 0: K1 -> K2)
+    const int skip = knobs().k3_skip;                     // timing experiments only (FFR_K3_SKIP: phases left out, WRONG results)
     if (vec) FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<true>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev));
+                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev, skip));
     else     FFR_CUDA_TRY(cudaLaunchKernelEx(&cfg, recheck_kernel<false>, ref, n_ref, cand, dim, thr, ref_index_base, keep, idx, val,
-                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev));
+                                             lists, band_tol, band_count, band_rows, band_cap, ref_map, n_unique_dev, skip));
     FFR_LAUNCH_CHECK("recheck");
     return FFR_OK;
 }

@@ -220,7 +220,7 @@ def test_filter_mma_unnormalised_inputs(ops):
     _check_cosine(ops, ref, cand, 0.5)
 
 
-@pytest.mark.parametrize("copies", [2, 3, 4, 6])
+@pytest.mark.parametrize("copies", [2, 3, 4, 6, 12])
 def test_filter_mma_exact_ties_pick_first(ops, copies):
     """Duplicated references give exactly equal scores: best_idx must be the FIRST occurrence (np.argmax).  Up to three
     equal leaders are resolved by the three-candidate fp32 check (K3a); four or more force the full fp32 rescan (K3b)."""
@@ -238,11 +238,14 @@ def test_filter_mma_exact_ties_pick_first(ops, copies):
     gap, _ = _top2_gap64(base, cand)
     assert np.array_equal(idx[gap > TIE_EPS], io[gap > TIE_EPS])
     if copies >= 4:
-        # every row has >= 4 scores inside the window: the copies inside ONE 128-column part are resolved by K3's part
-        # rescan, copies spread over two parts need every reference
+        # every row has >= 4 scores inside the window: the copies inside ONE 128-column part -- or two ADJACENT parts (6
+        # copies = 240 references), joined when the column halves are merged -- are resolved by K3's part rescan; copies
+        # spread over three or more parts (12 copies = 480 references) need every reference
         assert res.stats["part_rescans"] + res.stats["full_rescans"] >= 900
-        if copies >= 6:
+        if copies >= 10:
             assert res.stats["full_rescans"] >= 700
+        elif copies >= 6:
+            assert res.stats["part_rescans"] >= 700 and res.stats["full_rescans"] == 0
     else:
         assert res.stats["rechecked"] + res.stats["part_rescans"] >= 900
 
@@ -535,6 +538,34 @@ def test_duplicate_heavy_gallery_is_folded(ops, ffr_env, n_ref, n_cand, dim, cop
     assert torch.equal(r0.best_idx[:2000][ok], r1.best_idx[:2000][ok]) and torch.equal(r0.keep[:2000], r1.keep[:2000])
 
 
+@pytest.mark.parametrize("n_id,n_cand,dim", [(800, 80_000, 128), (1200, 40_000, 512), (7000, 30_000, 128)])
+def test_near_duplicate_groups_across_part_boundaries(ops, n_id, n_cand, dim):
+    """Five near-identical (cos 0.99995, NOT bit-equal) enrolments per identity, consecutive rows: every candidate of an
+    identity has five scores inside the fp16 window, all in one 128-column part -- or, for the groups that straddle a part
+    boundary (5 does not divide 128), in two ADJACENT parts, which the two column halves of the epilogue see separately.
+    The merge of the halves joins adjacent parts into one record, so those rows get a two-part rescan instead of the fp32
+    walk over every reference.  Parity with the oracle as everywhere; the full-rescan list stays (nearly) empty."""
+    rng = np.random.default_rng(n_id + dim)
+    base = rng.standard_normal((n_id, dim)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    sib = np.repeat(base, 5, axis=0)
+    jit = rng.standard_normal(sib.shape).astype(np.float32)
+    jit -= (jit * sib).sum(1, keepdims=True) * sib
+    jit /= np.linalg.norm(jit, axis=1, keepdims=True)
+    c = 0.99995
+    ref = (c * sib + np.sqrt(1 - c * c) * jit).astype(np.float32)
+    ref[::5] = base                                              # the first enrolment is the clean one
+    cand = rng.standard_normal((n_cand, dim)).astype(np.float32)
+    hit = rng.integers(0, n_id, n_cand // 2)
+    noise = rng.standard_normal((len(hit), dim)).astype(np.float32)
+    cand[::2][: len(hit)] = base[hit] + np.float32(0.6 / np.sqrt(dim)) * noise      # cos ~ 0.86 to its identity
+    sample = rng.choice(n_cand, 3000, replace=False)
+    res = _check_cosine(ops, ref, cand, 0.5, sample=sample)
+    st = res.stats
+    assert st["part_rescans"] > n_cand // 4, st                  # every planted row has several leaders inside the window
+    assert st["full_rescans"] < n_cand // 100, st                # ... and (nearly) none of them needs every reference
+
+
 # ---------------------------------------------------------------- small galleries through the fused stage32 schedule (round 2)
 @pytest.mark.parametrize("n_ref,n_cand,dim,offload", [
     (128, 75_776 + 77, 128, "auto"), (128, 113_704, 128, "1"), (64, 76_000, 72, "auto"), (32, 80_000, 128, "1"),
@@ -553,3 +584,48 @@ def test_small_galleries_fused(ops, ffr_env, n_ref, n_cand, dim, offload):
     sample = np.unique(np.concatenate([sample, np.arange(n_cand - 300, n_cand)]))          # the ragged tail in full
     res = _check_cosine(ops, ref, cand, 0.5, sample=sample)
     assert res.stats["k2"]["normalise"].startswith("stage32"), res.stats
+
+
+def test_host_pipeline_folds_duplicates_once_per_call(ops):
+    """ffr_ctx_filter_host with a duplicate-heavy gallery: the fold runs once per call (not per chunk), every chunk's K2 scans
+    the unique rows, and the answers equal the device path's (which equal the oracle's, test above)."""
+    rng = np.random.default_rng(17)
+    n_id, copies, dim, n_cand = 750, 8, 128, 340_000
+    base = rng.standard_normal((n_id, dim)).astype(np.float32)
+    ref = np.concatenate([base] * copies)[rng.permutation(n_id * copies)]
+    cand = rng.standard_normal((n_cand, dim)).astype(np.float32)
+    hit = rng.integers(0, n_id, n_cand // 2)
+    cand[::2] = base[hit] + 0.35 * rng.standard_normal((n_cand // 2, dim)).astype(np.float32)
+    hf = ops.HostFilter(device=0, max_ref=len(ref), chunk_cand=100_000, max_dim=dim)
+    keep, idx, val = hf(ref, cand, 0.5)
+    hf.close()
+    res = ops.face_filter(torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda(), 0.5, want_stats=True)
+    assert res.stats["refs_scanned"] == n_id
+    gap, _ = _top2_gap64(np.unique(ref, axis=0), cand[:3000])
+    ok = gap > TIE_EPS
+    assert np.array_equal(idx[:3000][ok], res.best_idx.cpu().numpy()[:3000][ok])
+    assert np.array_equal(keep, res.keep.cpu().numpy())
+    first = {}
+    for i, r in enumerate(ref):
+        first.setdefault(r.tobytes(), i)
+    assert all(first[ref[j].tobytes()] == j for j in idx[:20_000:7])          # every reported index is a FIRST occurrence
+
+
+def test_graphed_filter_replays_the_eager_result(ops):
+    """GraphedFilter.capture: K1 -> K2 -> K3 (programmatic dependent launch edges included) replayed as one CUDA graph over the
+    caller's tensors gives the eager call's outputs, also after the inputs changed in place."""
+    ref, cand = oracle.make_synthetic(1000, 100_000, 128, seed=5, n_adversarial=500, n_dup_refs=10)
+    r_t, c_t = torch.from_numpy(ref).cuda(), torch.from_numpy(cand).cuda()
+    out = (torch.empty(len(cand), dtype=torch.uint8, device="cuda"), torch.empty(len(cand), dtype=torch.int32, device="cuda"),
+           torch.empty(len(cand), dtype=torch.float32, device="cuda"))
+    g = ops.GraphedFilter.capture(r_t, c_t, 0.5, out=out)
+    assert g.launches == 3
+    for trial in range(3):
+        if trial:
+            c_t.copy_(c_t.roll(trial * 12_345, dims=0))
+        g.replay()
+        torch.cuda.synchronize()
+        got = [t.clone() for t in out]
+        eager = ops.face_filter(r_t, c_t, 0.5)
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], eager.keep) and torch.equal(got[1], eager.best_idx) and torch.equal(got[2], eager.best_val)
