@@ -63,6 +63,51 @@ def test_first_match_stream_matches_reference_tracker(ops, golden_dir, tag, metr
     assert np.array_equal(f2, want_found)
 
 
+def _tracker_stream(n_id, n_q, dim, seed):
+    """Noisy re-appearances of n_id identities (cosine ~0.94 to their identity, ~0 to the others), random order."""
+    rng = np.random.default_rng(seed)
+    ids = rng.standard_normal((n_id, dim)).astype(np.float32)
+    ids /= np.linalg.norm(ids, axis=1, keepdims=True)
+    who = rng.integers(0, n_id, n_q)
+    q = ids[who] + np.float32(0.35 / np.sqrt(dim)) * rng.standard_normal((n_q, dim)).astype(np.float32)
+    return (q * rng.uniform(0.5, 3.0, (n_q, 1))).astype(np.float32), who
+
+
+@pytest.mark.parametrize("metric,dim,n_id,n_q", [("cosine", 128, 40, 1500), ("cosine", 512, 70, 600), ("euclid", 256, 150, 900),
+                                                 ("cosine", 100, 300, 1200)])
+def test_first_match_stream_resident_and_l2_galleries_agree(ops, metric, dim, n_id, n_q):
+    """Round 2: a gallery whose whole capacity fits in shared memory lives there for the launch (write-through), larger ones are
+    scanned out of L2; 128 entries per round, the next query prefetched.  Both forms, one launch or many, give the trajectory
+    of the reference's scan restated in oracle.first_match_scan (+ its in-place update / append, :113-121)."""
+    q, _ = _tracker_stream(n_id, n_q, dim, seed=dim + n_id)
+    if metric == "euclid":
+        q /= np.linalg.norm(q, axis=1, keepdims=True)            # MobileFaceNet embeddings are unit vectors: dist < 0.72 <=> same face
+    small_cap = n_id + 8
+    assert (8 + small_cap) * (dim + 4) * 4 <= 200 * 1024   # the resident form
+    res = []
+    for cap, chunks in ((small_cap, 1), (4096, 1), (small_cap, 7)):
+        gal = ops.FaceGallery(dim, capacity=cap, metric=metric)
+        out = [gal.match(part) for part in np.array_split(q, chunks)]
+        res.append((np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out]), len(gal),
+                    gal.feat[:len(gal)].cpu().numpy()))
+    for r in res[1:]:
+        assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1]) and r[2] == res[0][2]
+        assert np.array_equal(r[3], res[0][3])                   # the global copy of the gallery is current after every launch
+    gallery, want_found, want_id = [], [], []
+    m = oracle.METRIC_EUCLID if metric == "euclid" else oracle.METRIC_COSINE
+    for x in q[:400]:
+        found, pos = oracle.first_match_scan(gallery, x, m)
+        if found:
+            gallery[pos] = x
+        else:
+            gallery.append(x)
+            pos = len(gallery) - 1
+        want_found.append(found)
+        want_id.append(pos + 1)
+    assert np.array_equal(res[0][0][:400], np.array(want_found)) and np.array_equal(res[0][1][:400], np.array(want_id))
+    assert res[0][2] <= n_id + n_id // 4 + 8                     # (nearly) every re-appearance was recognised
+
+
 def test_first_match_capacity_and_no_bbox(ops):
     rng = np.random.default_rng(1)
     x = rng.standard_normal((10, 64)).astype(np.float32)

@@ -202,7 +202,7 @@ if __name__ == "__main__":
                 perf(*shape, iters=3)
         delenv("FFR_STAGE32")
     if "--st32prof" in sys.argv:
-        for d in ("0", "2"):
+        for d in ("0", "1", "2", "3"):
             setenv("FFR_NORM_DIAG", d)
             print(" FFR_NORM_DIAG", d)
             prof(256, 2_000_000, 128)
