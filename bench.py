@@ -17,7 +17,7 @@ denominator; dup8 / near8 = cfg3's shape with a duplicate-heavy gallery (every i
 
 What the line carries beyond the contract: ``verified`` (every rank checks a >= 10 k-row sample of what it timed against
 the CPU oracle, and at N > 1 that rank r's slice of the gathered result is rank r's local result), ``secondary`` (short
-runs of cfg1 / hbm256 / cfg4 / n1 with their own rooflines, N = 1 only) and ``strong_scaling`` (the N-GPU job's candidates on one
+runs of cfg1 / hbm256 / cfg4 / dup8 / near8 / n1 with their own rooflines, N = 1 only) and ``strong_scaling`` (the N-GPU job's candidates on one
 GPU, measured in the same run).
 """
 from __future__ import annotations
@@ -510,8 +510,11 @@ def details_of(r, world):
                    f"rotating {r['n_buf']} input copies ({r['n_buf'] * r['in_bytes'] / 1e6:.0f} MB > L2 126 MB)"),
             "launch": "one CUDA graph per step (K1 -> K2 -> K3 captured once per rotating input)" if r["graph"] else "eager launches",
             "data": "half planted matches (cos 0.55-0.95), adversarial rows within +-2e-3 of the threshold every "
-                    f"{r['w'].get('adv_every', 0)} rows, {r['w'].get('n_dup', 0)} exactly duplicated references "
-                    "(~1e3 candidate rows with an exact tie)",
+                    f"{r['w'].get('adv_every', 0)} rows, " +
+                    (f"duplicate-heavy gallery: identities of {r['w']['dup_group']} consecutive rows, {r['w']['dup_group'] // 2} exact copies + "
+                     f"{r['w']['dup_group'] - r['w']['dup_group'] // 2} enrolments at cosine {r['w'].get('sib_cos', 0.9)} (every matched row has several leaders)"
+                     if r['w'].get('dup_group', 0) > 1 else
+                     f"{r['w'].get('n_dup', 0)} exactly duplicated references (~1e3 candidate rows with an exact tie)"),
             "keep_fraction": r["keep_frac"], "recheck": r["stats"]}
 
 
@@ -525,7 +528,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the short cfg1 / hbm256 / cfg4 / n1 runs of the default line")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short cfg1 / hbm256 / cfg4 / dup8 / near8 / n1 runs of the default line")
     ap.add_argument("--no-strong", action="store_true", help="skip the one-GPU run of the whole N-GPU job")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
@@ -633,7 +636,7 @@ def main():
         except NameError:
             pass
         secondary = {}
-        for key in ("cfg1", "hbm256", "cfg4", "n1"):
+        for key in ("cfg1", "hbm256", "cfg4", "dup8", "near8", "n1"):
             torch.cuda.empty_cache()
             # (cfg1 is ~25 us per step: enough steps that the GPU leaves its idle clocks; the others are ms-sized)
             sec_steps, sec_warm = (64, 64) if key == "cfg1" else (5, 3)
