@@ -941,26 +941,37 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                     // ulp in rare elements, like x * (1/|x|) differs from K1's x / |x|), one IEEE sqrt + division, then 16 STS.128.
                     // (Round 1 read every row twice in compact loops to keep the code small; with the tail's work moved into these
                     // warps their time per tile matters, and half the shared-memory reads is what pays.)
+                    // Packed fp32 (FFMA2 / FMUL2, sm_100): the warp's time per buffer is its own instruction stream (ncu: one
+                    // warp, IPC 0.34, two thirds of the instructions on the FMA pipe), so the 128 squares and the 128 scalings are
+                    // issued two per instruction.  Products and the scaled values are the same IEEE results; the sum of squares is
+                    // kept in eight partial sums instead of four (1 / |x| can differ in the last place from the earlier form).
+                    // The timing-only knobs (no loads / no stores) exist in the instrumented build alone: as a run-time select they
+                    // cost 63 register-clearing instructions per buffer.
+                    const bool diag_noload = kInstr && (p.norm_diag & 1), diag_nostore = kInstr && (p.norm_diag & 2);
                     float4 x[32];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const uint8_t* sg = src + g * (kStageBytes / 4);
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
-                            x[g * 8 + c] = (p.norm_diag & 1) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                                             : *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(c) << 4) ^ sw));
+                            x[g * 8 + c] = diag_noload ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                       : *reinterpret_cast<const float4*>(sg + ((static_cast<uint32_t>(c) << 4) ^ sw));
                     }
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                    float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        q0 = fmaf(x[c].x, x[c].x, q0); q0 = fmaf(x[c].y, x[c].y, q0); q0 = fmaf(x[c].z, x[c].z, q0); q0 = fmaf(x[c].w, x[c].w, q0);
-                        q1 = fmaf(x[c + 1].x, x[c + 1].x, q1); q1 = fmaf(x[c + 1].y, x[c + 1].y, q1); q1 = fmaf(x[c + 1].z, x[c + 1].z, q1); q1 = fmaf(x[c + 1].w, x[c + 1].w, q1);
-                        q2 = fmaf(x[c + 2].x, x[c + 2].x, q2); q2 = fmaf(x[c + 2].y, x[c + 2].y, q2); q2 = fmaf(x[c + 2].z, x[c + 2].z, q2); q2 = fmaf(x[c + 2].w, x[c + 2].w, q2);
-                        q3 = fmaf(x[c + 3].x, x[c + 3].x, q3); q3 = fmaf(x[c + 3].y, x[c + 3].y, q3); q3 = fmaf(x[c + 3].z, x[c + 3].z, q3); q3 = fmaf(x[c + 3].w, x[c + 3].w, q3);
+                    for (int c = 0; c < 32; c += 2) {
+                        const float2 a0 = make_float2(x[c].x, x[c].y), a1 = make_float2(x[c].z, x[c].w);
+                        const float2 b0 = make_float2(x[c + 1].x, x[c + 1].y), b1 = make_float2(x[c + 1].z, x[c + 1].w);
+                        q0 = __ffma2_rn(a0, a0, q0);
+                        q1 = __ffma2_rn(a1, a1, q1);
+                        q2 = __ffma2_rn(b0, b0, q2);
+                        q3 = __ffma2_rn(b1, b1, q3);
                     }
                     const int r = part * kStageRows + lane;                               // row inside the tile
                     // rows past the end stay zero
-                    const float inv = (row0 + r < p.n_cand) ? __fdiv_rn(1.0f, sqrtf((q0 + q1) + (q2 + q3))) : 0.f;
+                    const float qq = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+                    const float inv = (row0 + r < p.n_cand) ? __fdiv_rn(1.0f, sqrtf(qq)) : 0.f;
+                    const float2 inv2 = make_float2(inv, inv);
                     uint8_t* dst = smem_a + as * a_stage_bytes + r * 128;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {                                         // 32 input floats -> 4 chunks of 8 halves
@@ -968,16 +979,18 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float4 lo = x[g * 8 + 2 * c], hi = x[g * 8 + 2 * c + 1];
-                            const __half2 h0 = __floats2half2_rn(lo.x * inv, lo.y * inv);
-                            const __half2 h1 = __floats2half2_rn(lo.z * inv, lo.w * inv);
-                            const __half2 h2 = __floats2half2_rn(hi.x * inv, hi.y * inv);
-                            const __half2 h3 = __floats2half2_rn(hi.z * inv, hi.w * inv);
+                            const float2 s0 = __fmul2_rn(make_float2(lo.x, lo.y), inv2), s1 = __fmul2_rn(make_float2(lo.z, lo.w), inv2);
+                            const float2 s2 = __fmul2_rn(make_float2(hi.x, hi.y), inv2), s3 = __fmul2_rn(make_float2(hi.z, hi.w), inv2);
+                            const __half2 h0 = __floats2half2_rn(s0.x, s0.y);
+                            const __half2 h1 = __floats2half2_rn(s1.x, s1.y);
+                            const __half2 h2 = __floats2half2_rn(s2.x, s2.y);
+                            const __half2 h3 = __floats2half2_rn(s3.x, s3.y);
                             uint4 pk;
                             pk.x = *reinterpret_cast<const uint32_t*>(&h0);
                             pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                             pk.z = *reinterpret_cast<const uint32_t*>(&h2);
                             pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-                            if (!(p.norm_diag & 2)) *reinterpret_cast<uint4*>(dg + ((static_cast<uint32_t>(4 * (g & 1) + c) << 4) ^ sw)) = pk;
+                            if (!diag_nostore) *reinterpret_cast<uint4*>(dg + ((static_cast<uint32_t>(4 * (g & 1) + c) << 4) ^ sw)) = pk;
                         }
                     }
                     __syncwarp();
