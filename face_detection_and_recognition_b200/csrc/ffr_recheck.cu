@@ -551,10 +551,16 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
             const int64_t slot = g * kFullGroup + w;
             float cc = 0.f;
             if (slot < count) {
+                // kVec: parked TRANSPOSED, [dim][kFullGroup] -- the eight candidates' values of one k are two float4, i.e. four
+                // (candidate j, candidate j + 1) pairs for the packed FMAs below
                 const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
-                for (int d = lane; d < dim; d += 32) { const float t = __ldg(c + d); s_c[w * dim + d] = t; cc = fmaf(t, t, cc); }
+                for (int d = lane; d < dim; d += 32) {
+                    const float t = __ldg(c + d);
+                    s_c[kVec ? d * kFullGroup + w : w * dim + d] = t;
+                    cc = fmaf(t, t, cc);
+                }
             } else {
-                for (int d = lane; d < dim; d += 32) s_c[w * dim + d] = 0.f;
+                for (int d = lane; d < dim; d += 32) s_c[kVec ? d * kFullGroup + w : w * dim + d] = 0.f;
             }
             cc = warp_sum(cc);
             if (lane == 0) s_ccs[w] = __fsqrt_rn(cc);
@@ -571,25 +577,35 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
             // prefetched into registers while the current one is consumed, and every thread owns a register tile of
             // kRefsPerThread references (t, t + 256, ...) x kFullGroup candidates: per 8 K-values it issues 8 + 16
             // shared loads for 256 FMAs (the candidate loads are warp-wide broadcasts).
-            float* s_r = s_c + kFullGroup * dim;
+            // (round 2: the tiles go global -> shared with cp.async into TWO buffers -- no staging registers, no shared-memory
+            // stores by the threads, one barrier per chunk instead of two)
+            float* s_r0 = s_c + kFullGroup * dim;
+            constexpr int kTileFloats = kTileRefs * kKCPad;
             const int n_kc = (dim + kKC - 1) / kKC;
             const int64_t n_rt = (hi - lo + kTileRefs - 1) / kTileRefs;
             const int64_t n_it = n_rt * n_kc;
-            constexpr int kPf = kTileRefs * (kKC / 4) / kThreads;          // float4 per thread per chunk (8)
-            float4 pf[kPf];
-            auto fetch = [&](int64_t rt, int kc) {
+            constexpr int kPf = kTileRefs * (kKC / 4) / kThreads;          // 16-byte pieces per thread per chunk (8)
+            auto fetch = [&](int64_t rt, int kc, int buf) {
                 const int64_t i0 = lo + rt * kTileRefs;
+                float* dst = s_r0 + buf * kTileFloats;
 #pragma unroll
                 for (int u = 0; u < kPf; ++u) {
                     const int f = threadIdx.x + kThreads * u;              // 2 float4 per reference row
                     const int64_t gi = i0 + (f >> 1);
                     const int col = kc * kKC + (f & 1) * 4;
-                    pf[u] = (gi < hi && col < dim) ? __ldg(reinterpret_cast<const float4*>(ref + gi * dim + col))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool ok = gi < hi && col < dim;
+                    // (src-size 0 = the 16 bytes are zero-filled: rows past the slice, columns past dim)
+                    const float* src = ok ? ref + gi * dim + col : ref;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                                 ::"r"(smem_u32(dst + (f >> 1) * kKCPad + (f & 1) * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            fetch(0, 0);
-            float acc[kRefsPerThread][kFullGroup];
+            fetch(0, 0, 0);
+            // accumulators as (candidate 2p, candidate 2p + 1) pairs: one FFMA2 (sm_100 packed fp32) per pair and k -- the same
+            // IEEE fma per candidate, in the same order over k, at half the FMA-pipe instructions (the walk is FMA-issue-bound)
+            static_assert(kFullGroup == 8, "two float4 of candidates per k");
+            float2 acc[kRefsPerThread][kFullGroup / 2];
             float rr[kRefsPerThread];
             int64_t rt = 0;
             int kc = 0;
@@ -599,36 +615,38 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
                     for (int r = 0; r < kRefsPerThread; ++r) {
                         rr[r] = 0.f;
 #pragma unroll
-                        for (int j = 0; j < kFullGroup; ++j) acc[r][j] = 0.f;
+                        for (int j = 0; j < kFullGroup / 2; ++j) acc[r][j] = make_float2(0.f, 0.f);
                     }
                 }
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < kPf; ++u) {
-                    const int f = threadIdx.x + kThreads * u;
-                    *reinterpret_cast<float4*>(s_r + (f >> 1) * kKCPad + (f & 1) * 4) = pf[u];
-                }
-                __syncthreads();
+                asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's pieces of chunk `it` have landed ...
+                __syncthreads();                                         // ... everybody's have, and chunk it - 1 has been consumed
+                const float* s_r = s_r0 + static_cast<int>(it & 1) * kTileFloats;
                 int nkc = kc + 1;
                 int64_t nrt = rt;
                 if (nkc == n_kc) { nkc = 0; ++nrt; }
-                if (it + 1 < n_it) fetch(nrt, nkc);
+                if (it + 1 < n_it) fetch(nrt, nkc, static_cast<int>((it + 1) & 1));   // in flight while this chunk is consumed
 #pragma unroll
                 for (int j4 = 0; j4 < kKC / 4; ++j4) {
                     const int col = kc * kKC + j4 * 4;
                     if (col < dim) {
-                        float4 cv[kFullGroup];
-#pragma unroll
-                        for (int j = 0; j < kFullGroup; ++j) cv[j] = *reinterpret_cast<const float4*>(s_c + j * dim + col);
+                        float rv[kRefsPerThread][4];
 #pragma unroll
                         for (int r = 0; r < kRefsPerThread; ++r) {
-                            const float4 rv = *reinterpret_cast<const float4*>(s_r + (threadIdx.x + r * kThreads) * kKCPad + j4 * 4);
-                            rr[r] = fmaf(rv.x, rv.x, rr[r]); rr[r] = fmaf(rv.y, rv.y, rr[r]);
-                            rr[r] = fmaf(rv.z, rv.z, rr[r]); rr[r] = fmaf(rv.w, rv.w, rr[r]);
+                            const float4 t = *reinterpret_cast<const float4*>(s_r + (threadIdx.x + r * kThreads) * kKCPad + j4 * 4);
+                            rv[r][0] = t.x; rv[r][1] = t.y; rv[r][2] = t.z; rv[r][3] = t.w;
+                            rr[r] = fmaf(t.x, t.x, rr[r]); rr[r] = fmaf(t.y, t.y, rr[r]);
+                            rr[r] = fmaf(t.z, t.z, rr[r]); rr[r] = fmaf(t.w, t.w, rr[r]);
+                        }
 #pragma unroll
-                            for (int j = 0; j < kFullGroup; ++j) {
-                                acc[r][j] = fmaf(cv[j].x, rv.x, acc[r][j]); acc[r][j] = fmaf(cv[j].y, rv.y, acc[r][j]);
-                                acc[r][j] = fmaf(cv[j].z, rv.z, acc[r][j]); acc[r][j] = fmaf(cv[j].w, rv.w, acc[r][j]);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const float4 ca = *reinterpret_cast<const float4*>(s_c + (col + kk) * kFullGroup);
+                            const float4 cb = *reinterpret_cast<const float4*>(s_c + (col + kk) * kFullGroup + 4);
+                            const float2 cp[4] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y), make_float2(cb.z, cb.w)};
+#pragma unroll
+                            for (int r = 0; r < kRefsPerThread; ++r) {
+                                const float2 r2 = make_float2(rv[r][kk], rv[r][kk]);
+#pragma unroll
+                                for (int pj = 0; pj < kFullGroup / 2; ++pj) acc[r][pj] = __ffma2_rn(cp[pj], r2, acc[r][pj]);
                             }
                         }
                     }
@@ -641,7 +659,8 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
                             const float rs = __fsqrt_rn(rr[r]);
 #pragma unroll
                             for (int j = 0; j < kFullGroup; ++j) {
-                                const float sc = __fdiv_rn(acc[r][j], __fmul_rn(rs, s_ccs[j]));
+                                const float dot = (j & 1) ? acc[r][j >> 1].y : acc[r][j >> 1].x;
+                                const float sc = __fdiv_rn(dot, __fmul_rn(rs, s_ccs[j]));
                                 if (sc > best[j]) { best[j] = sc; bidx[j] = static_cast<int32_t>(i); }
                             }
                         }
@@ -750,14 +769,14 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
     // the flagged-row counts live on the device: ONE fixed grid strides over both lists (blocks without work exit at once)
     const int64_t gx = static_cast<int64_t>(sms) * 2;         // two blocks per SM are resident (registers): one wave
     const dim3 g2(static_cast<unsigned>(gx));
-    const size_t smem_full = smem + static_cast<size_t>(kTileRefs) * kKCPad * sizeof(float);
+    const size_t smem_full = smem + 2 * static_cast<size_t>(kTileRefs) * kKCPad * sizeof(float);   // + two cp.async tile buffers
     {   // per-DEVICE function attribute: once for every device this process uses
         static std::mutex mu;
         static bool attr_set[kMaxDevices] = {};
         const int slot = current_device_slot();
         std::lock_guard<std::mutex> lock(mu);
         if (!attr_set[slot]) {
-            FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 148 * 1024));
             attr_set[slot] = true;
         }
     }
