@@ -55,7 +55,7 @@ struct RecheckRec {     // pair record (K3a)                                  | 
 
 // rows whose third-best score is also within delta: rescanned against every reference in fp32 (K3b).
 // K2 appends the row, zeroes its packed-result key and the arrival counter of its group of kFullGroup rows.
-constexpr int kFullGroup = 8;
+constexpr int kFullGroup = 16;
 struct WsHeader;
 struct RecheckLists {
     WsHeader* hdr;

@@ -20,7 +20,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kKC = 8;             // floats per staged reference chunk (two float4)
 constexpr int kKCPad = 12;         // padded row stride (48 B): conflict-free float4 reads, 16-byte aligned
-constexpr int kRefsPerThread = 4;  // register tile: 4 references x kFullGroup candidates per thread
+constexpr int kRefsPerThread = 2;  // register tile: 2 references x kFullGroup (16) candidates per thread
 constexpr int kTileRefs = kThreads * kRefsPerThread;   // 1024 references staged per tile
 
 __device__ __forceinline__ float cos_fp32(const float* __restrict__ c_smem, const float* __restrict__ r, int32_t dim,
@@ -547,23 +547,25 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
         const int64_t lo = slice * kSliceRefs;
         const int64_t hi = (lo + kSliceRefs < n_ref) ? lo + kSliceRefs : n_ref;
         __syncthreads();
-        if (g != parked) {                                     // warp w parks candidate row w of the group
-            const int64_t slot = g * kFullGroup + w;
-            float cc = 0.f;
-            if (slot < count) {
-                // kVec: parked TRANSPOSED, [dim][kFullGroup] -- the eight candidates' values of one k are two float4, i.e. four
-                // (candidate j, candidate j + 1) pairs for the packed FMAs below
-                const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
-                for (int d = lane; d < dim; d += 32) {
-                    const float t = __ldg(c + d);
-                    s_c[kVec ? d * kFullGroup + w : w * dim + d] = t;
-                    cc = fmaf(t, t, cc);
+        if (g != parked) {                                     // warp w parks candidate rows w, w + kWarps, ... of the group
+            for (int jw = w; jw < kFullGroup; jw += kWarps) {
+                const int64_t slot = g * kFullGroup + jw;
+                float cc = 0.f;
+                if (slot < count) {
+                    // kVec: parked TRANSPOSED, [dim][kFullGroup] -- the sixteen candidates' values of one k are four float4, i.e.
+                    // eight (candidate j, candidate j + 1) pairs for the packed FMAs below
+                    const float* c = cand + static_cast<int64_t>(lists.full_rows[slot]) * dim;
+                    for (int d = lane; d < dim; d += 32) {
+                        const float t = __ldg(c + d);
+                        s_c[kVec ? d * kFullGroup + jw : jw * dim + d] = t;
+                        cc = fmaf(t, t, cc);
+                    }
+                } else {
+                    for (int d = lane; d < dim; d += 32) s_c[kVec ? d * kFullGroup + jw : jw * dim + d] = 0.f;
                 }
-            } else {
-                for (int d = lane; d < dim; d += 32) s_c[kVec ? d * kFullGroup + w : w * dim + d] = 0.f;
+                cc = warp_sum(cc);
+                if (lane == 0) s_ccs[jw] = __fsqrt_rn(cc);
             }
-            cc = warp_sum(cc);
-            if (lane == 0) s_ccs[w] = __fsqrt_rn(cc);
             parked = g;
         }
         __syncthreads();
@@ -604,7 +606,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
             fetch(0, 0, 0);
             // accumulators as (candidate 2p, candidate 2p + 1) pairs: one FFMA2 (sm_100 packed fp32) per pair and k -- the same
             // IEEE fma per candidate, in the same order over k, at half the FMA-pipe instructions (the walk is FMA-issue-bound)
-            static_assert(kFullGroup == 8, "two float4 of candidates per k");
+            static_assert(kFullGroup == 16, "four float4 of candidates per k");
             float2 acc[kRefsPerThread][kFullGroup / 2];
             float rr[kRefsPerThread];
             int64_t rt = 0;
@@ -639,9 +641,13 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
                         }
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const float4 ca = *reinterpret_cast<const float4*>(s_c + (col + kk) * kFullGroup);
-                            const float4 cb = *reinterpret_cast<const float4*>(s_c + (col + kk) * kFullGroup + 4);
-                            const float2 cp[4] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y), make_float2(cb.z, cb.w)};
+                            float2 cp[kFullGroup / 2];
+#pragma unroll
+                            for (int q4 = 0; q4 < kFullGroup / 4; ++q4) {
+                                const float4 c4 = *reinterpret_cast<const float4*>(s_c + (col + kk) * kFullGroup + q4 * 4);
+                                cp[2 * q4] = make_float2(c4.x, c4.y);
+                                cp[2 * q4 + 1] = make_float2(c4.z, c4.w);
+                            }
 #pragma unroll
                             for (int r = 0; r < kRefsPerThread; ++r) {
                                 const float2 r2 = make_float2(rv[r][kk], rv[r][kk]);
@@ -761,10 +767,11 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
                    float band_tol, int32_t* band_count, int64_t* band_rows, int64_t band_cap,
                    const int32_t* ref_map, const int32_t* n_unique_dev, cudaStream_t s) {
     if (n_cand == 0) return FFR_OK;
-    static_assert(kWarps == kFullGroup, "one warp parks one candidate row of a full-rescan group");
+    static_assert(kFullGroup % kWarps == 0, "every warp parks kFullGroup / kWarps candidate rows of a full-rescan group");
     const int sms = num_sms();
-    const size_t smem = static_cast<size_t>(kWarps) * dim * sizeof(float);
-    if (smem > 48 * 1024) { set_error("recheck: dim %d too large", dim); return FFR_ERR_UNSUPPORTED; }
+    // kFullGroup parked candidate rows (the per-warp phases use the first kWarps of them)
+    const size_t smem = static_cast<size_t>(kFullGroup) * dim * sizeof(float);
+    if (smem > 96 * 1024) { set_error("recheck: dim %d too large", dim); return FFR_ERR_UNSUPPORTED; }
     const int vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(ref) & 15) == 0);
     // the flagged-row counts live on the device: ONE fixed grid strides over both lists (blocks without work exit at once)
     const int64_t gx = static_cast<int64_t>(sms) * 2;         // two blocks per SM are resident (registers): one wave
@@ -777,6 +784,7 @@ int launch_recheck(const float* ref, int64_t n_ref, const float* cand, int64_t n
         std::lock_guard<std::mutex> lock(mu);
         if (!attr_set[slot]) {
             FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 148 * 1024));
+            FFR_CUDA_TRY(cudaFuncSetAttribute(recheck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 148 * 1024));
             attr_set[slot] = true;
         }
     }
