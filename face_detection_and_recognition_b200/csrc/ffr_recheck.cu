@@ -538,14 +538,18 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
         return;
     }
     __syncthreads();                                            // phase A's per-warp rows are dead: the tiled walk reuses s_c
-    const int64_t n_slices = (n_ref + kSliceRefs - 1) / kSliceRefs;
+    // duplicate references folded before K2 (ref_map: compact column -> original row, ascending): the walk visits the UNIQUE
+    // rows only -- a later bit-identical copy can never be the first occurrence of the maximum -- and works on compact
+    // indices (their order is the original order), mapped back when a row's result is written
+    const int64_t n_walk = n_unique_dev != nullptr ? static_cast<int64_t>(__ldg(n_unique_dev)) : n_ref;
+    const int64_t n_slices = (n_walk + kSliceRefs - 1) / kSliceRefs;
     const int64_t n_groups = (count + kFullGroup - 1) / kFullGroup;
     const int64_t n_items = n_groups * n_slices;
     int64_t parked = -1;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t g = item / n_slices, slice = item - g * n_slices;
         const int64_t lo = slice * kSliceRefs;
-        const int64_t hi = (lo + kSliceRefs < n_ref) ? lo + kSliceRefs : n_ref;
+        const int64_t hi = (lo + kSliceRefs < n_walk) ? lo + kSliceRefs : n_walk;
         __syncthreads();
         if (g != parked) {                                     // warp w parks candidate rows w, w + kWarps, ... of the group
             for (int jw = w; jw < kFullGroup; jw += kWarps) {
@@ -587,17 +591,24 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
             const int64_t n_rt = (hi - lo + kTileRefs - 1) / kTileRefs;
             const int64_t n_it = n_rt * n_kc;
             constexpr int kPf = kTileRefs * (kKC / 4) / kThreads;          // 16-byte pieces per thread per chunk (8)
+            int64_t rowi[kPf];                                             // the rows this thread copies from, per reference tile
             auto fetch = [&](int64_t rt, int kc, int buf) {
                 const int64_t i0 = lo + rt * kTileRefs;
                 float* dst = s_r0 + buf * kTileFloats;
+                if (kc == 0) {
+#pragma unroll
+                    for (int u = 0; u < kPf; ++u) {
+                        const int64_t gi = i0 + ((threadIdx.x + kThreads * u) >> 1);
+                        rowi[u] = gi < hi ? (ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + gi)) : gi) : -1;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < kPf; ++u) {
                     const int f = threadIdx.x + kThreads * u;              // 2 float4 per reference row
-                    const int64_t gi = i0 + (f >> 1);
                     const int col = kc * kKC + (f & 1) * 4;
-                    const bool ok = gi < hi && col < dim;
+                    const bool ok = rowi[u] >= 0 && col < dim;
                     // (src-size 0 = the 16 bytes are zero-filled: rows past the slice, columns past dim)
-                    const float* src = ok ? ref + gi * dim + col : ref;
+                    const float* src = ok ? ref + rowi[u] * dim + col : ref;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                                  ::"r"(smem_u32(dst + (f >> 1) * kKCPad + (f & 1) * 4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
                 }
@@ -681,7 +692,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
 #pragma unroll
                 for (int j = 0; j < kFullGroup; ++j) acc[j] = 0.f;
                 float rr = 0.f;
-                const float* r = ref + i * dim;
+                const float* r = ref + (ref_map != nullptr ? static_cast<int64_t>(__ldg(ref_map + i)) : i) * dim;
                 for (int k = 0; k < dim; ++k) {
                     const float rv = __ldg(r + k);
                     rr = fmaf(rv, rv, rr);
@@ -728,6 +739,7 @@ recheck_kernel(const float* __restrict__ ref, int64_t n_ref, const float* __rest
                 int32_t bi;
                 unpack_key(key, v, bi);
                 if (key == 0ull) { v = -INFINITY; bi = 0; }
+                else if (ref_map != nullptr) bi = __ldg(ref_map + bi);          // compact column -> original reference
                 emit_result(lists.full_rows[slot], v, bi, thr, ref_index_base, keep, best_idx, best_val, band_tol,
                             band_count, band_rows, band_cap);
             }
