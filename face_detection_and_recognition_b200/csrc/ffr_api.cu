@@ -90,6 +90,7 @@ const Knobs* read_knobs() {
     k->tail_offload = env_int("FFR_TAIL_OFFLOAD", -1);
     k->pdl = env_int("FFR_PDL", 1);
     k->cand_l2_mb = env_int("FFR_CAND_L2_MB", 0);      // stage32: candidate matrices up to this size (MiB) are loaded WITHOUT evict-first (measured: slower)
+    k->last_inline = env_int("FFR_LAST_INLINE", 1);    // stage32 with the offloaded tail: the CTA's last candidate tile is finished by the epilogue warps
     k->k3_skip = env_int("FFR_K3_SKIP", 0);            // timing experiments: K3 phases left out (1 pairs, 2 parts, 4 full) -- WRONG results
     return k;
 }

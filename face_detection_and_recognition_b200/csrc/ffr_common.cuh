@@ -39,7 +39,7 @@ constexpr int kMaxDevices = 64;
 struct Knobs {
     int cta_group, a_stages, b_stages, acc_stages, diag_half_b, epi_mode, discard_a, decouple_a,
         norm_evict_first, norm_diag, grid_update_refs, grid_exact, norm_ahead, fuse_k1, stage32, k1_blocks_per_sm,
-        k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, tail_offload, pdl, cand_l2_mb, k3_skip;
+        k1_subwarp, k1_rows, k2s_subwarp, dedup_refs, tail_offload, pdl, cand_l2_mb, k3_skip, last_inline;
 };
 const Knobs& knobs();
 void reload_knobs();

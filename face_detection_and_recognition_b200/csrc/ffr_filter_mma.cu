@@ -463,6 +463,7 @@ struct KParams {
     int stage32;                   // kNorm, dim_pad == 128: fp32 candidate rows are staged through shared memory by TMA and the normaliser
                                    // warps write the swizzled fp16 A tile directly (no global scratch, no K1 pass at ANY n_ref)
     int s_bufs;                    // stage32: staging ring depth (buffers of kStageRows rows)
+    int last_inline;               // kNormMode 2: the CTA's LAST candidate tile is merged + emitted by the epilogue warps themselves (FFR_LAST_INLINE)
     int discard_a;                 // kNorm: discard the consumed fp16 rows from L2 (FFR_DISCARD_A, default on)
     uint64_t cand32_policy;        // stage32: L2 policy of the fp32 candidate loads -- evict-first for a stream larger than L2, plain when the
                                    // whole candidate matrix fits (K3's fp32 re-check then finds its rows in L2 instead of HBM)
@@ -1009,7 +1010,8 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1; }
             }
             if (kOffload)
-                for (uint32_t u = n_done >= 2u ? n_done - 2u : 0u; u < n_done; ++u) merge_tile(u);   // drain: the last two tiles
+                // drain: the last two tiles (the very last one is merged by the epilogue warps themselves: last_inline)
+                for (uint32_t u = n_done >= 2u ? n_done - 2u : 0u; u + (p.last_inline != 0 ? 1u : 0u) < n_done; ++u) merge_tile(u);
             if (pr && lane == 0) {
                 p.prof[blockIdx.x * 32 + 13] = static_cast<unsigned long long>(clock64() - t_nv_begin);
                 p.prof[blockIdx.x * 32 + 14] = n_done;
@@ -1218,7 +1220,10 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
             // warps of ONE lane quadrant (ids 1+q / 5+q, alternating with the tile parity so that an early arrive for tile
             // n + 2 cannot complete tile n's barrier); with CTA-wide barriers every quadrant waited for the slowest warp.
             const long long t_tail0 = pr ? clock64() : 0;
-            if constexpr (kOffload) {
+            // ... except for the CTA's LAST candidate tile: nothing is left to overlap its tail with, and four merger warps (32 rows
+            // each) finish it in half the time the two helper warps (64 rows each) need -- the kernel's drain.
+            const bool inline_last = kOffload && p.last_inline != 0 && tile + tile_stride >= n_tiles;
+            if (kOffload && !inline_last) {
                 // stage32 with several reference tiles per candidate tile: the tail is NOT run here.  Merging the two column halves, classifying the row and appending to K3's
                 // lists is ~300 dependent instructions that used to stall this warp for as long as a reference tile's hot loop
                 // (with four reference tiles per candidate tile -- BASELINE configs[1] -- a fifth of the epilogue's time).  Both
@@ -1241,14 +1246,22 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&m_full[slot]);                  // (release at CTA scope: the warp's stores above)
             } else {
-            if (first_tile) {
+            float* xmerge = merge;                               // exchange buffer of the two column halves
+            if (kOffload) {
+                // (the parked-state slot this tile would have used, once the helper warps have emptied it)
+                const uint32_t slot = c_it & 1u;
+                mbar_wait(&m_empty[slot], ((c_it >> 1) & 1u) ^ 1u);
+                xmerge = merge + slot * 2 * 11 * kTileM;
+                pdl_wait();
+                if (blockIdx.x == 0 && threadIdx.x == 64) p.lists.hdr->refs_scanned = static_cast<int32_t>(n_ref);   // (a CTA with ONE tile: the helper warps never merge)
+            } else if (first_tile) {
                 pdl_wait();                                      // the re-check header the appends below count in is zeroed by K1
                 if (blockIdx.x == 0 && threadIdx.x == 64) p.lists.hdr->refs_scanned = static_cast<int32_t>(n_ref);
             }
             const bool merger = kAlt ? (((c_it ^ static_cast<uint32_t>(h)) & 1u) == 0u) : (h == 0);
             const uint32_t bar_ready = kAlt ? (1 + q + 4 * (c_it & 1u)) : (1 + q);
             if (!merger) {
-                float* mg = merge + (kAlt ? 0 : (h - 1) * 11 * kTileM);
+                float* mg = xmerge + (kAlt ? 0 : (h - 1) * 11 * kTileM);
                 if (!kAlt && !first_tile) named_bar_sync(5 + q, kParts * 32);  // merge buffer free again
                 mg[0 * kTileM + r_in_tile] = t.b1;
                 mg[1 * kTileM + r_in_tile] = t.b2;
@@ -1273,7 +1286,7 @@ filter_mma_kernel(const __grid_constant__ CUtensorMap tmap_cand, const __grid_co
                 HiddenM hm = hidden_single(hid);
 #pragma unroll
                 for (int pp = 0; pp < kParts - 1; ++pp) {
-                    const float* mg = merge + pp * 11 * kTileM;
+                    const float* mg = xmerge + pp * 11 * kTileM;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) ob[pp][e] = mg[e * kTileM + r_in_tile];
 #pragma unroll
@@ -1499,6 +1512,7 @@ int launch_filter_mma_impl(const __half* ref16, int64_t n_ref, __half* cand16, c
     p.decouple_a = kn.decouple_a;
     p.stage32 = st32 ? 1 : 0;
     p.s_bufs = s_bufs;
+    p.last_inline = kn.last_inline;
     p.cand32_policy = static_cast<double>(n_cand) * dim * 4.0 <= kn.cand_l2_mb * 1048576.0 ? kEvictNormal : kEvictFirst;
     p.norm_evict_first = kn.norm_evict_first;
     p.norm_diag = kn.norm_diag;
